@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MDE hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path
+
+A "step" is one iteration of MDE.embed() (>= 1 fused evaluation of the whole edge list, the
+projection(s), the L-BFGS update and the Wolfe line search).  Workload at N=1: BASELINE.json
+configs[1] -- the MNIST-shaped preserve_neighbors problem (n=70 000, m=2, ~1.55 M edges,
+PushAndPull(Log1p, Log), Centered) on synthetic data (no datasets / network here).  For N>1 the
+per-GPU edge shard is fixed at that size (weak scaling): rank r holds its own 1.55 M edges over the
+same 70 000 items, X is replicated and the gradient is all-reduced (NCCL) once per evaluation.
+
+JSON keys beyond the base contract: `roofline` (fused distortion kernel, cold L2, CUDA events),
+`cpu_baseline` (reference or oracle port on the host cores, bounded sample), `e2e` (public API with
+pinned HOST buffers, copies inside the timed region), `gpu_launches`, `clocks`, `iters_per_sec`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_ITEMS, EMBED_DIM, K_NEIGHBORS = 70000, 2, 15
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic MNIST-shaped problem
+# ------------------------------------------------------------------------------------------
+def c2_edges(seed, n=N_ITEMS, k=K_NEIGHBORS):
+    """Attractive: per item k pseudo-neighbours with index locality inside 10 'classes',
+    symmetrised + de-duplicated the way Graph.from_edges does (duplicates summed => w in {1,2},
+    sorted by (i,j); pymde/preprocess/graph.py:21-72).  Repulsive: as many uniformly sampled
+    non-neighbour pairs, w = -1, appended unsorted (pymde/recipes.py:388-416)."""
+    rng = np.random.default_rng(seed)
+    blob = n // 10
+    i = np.repeat(np.arange(n, dtype=np.int64), k)
+    # two-sided local offsets: ~half of the directed picks are reciprocated, as in a real k-NN
+    # graph (MNIST: 70 000 x 15 directed -> 776 k undirected edges, examples/mnist.ipynb:56)
+    off = rng.integers(1, 24, n * k) * rng.choice([-1, 1], n * k)
+    j = (i // blob) * blob + ((i % blob) + off) % blob
+    lo, hi = np.minimum(i, j), np.maximum(i, j)
+    key = lo * n + hi
+    uniq, counts = np.unique(key, return_counts=True)
+    att = np.stack([uniq // n, uniq % n], 1)
+    w_att = counts.astype(np.float32).clip(max=2.0)
+    n_rep = len(att)
+    cand = rng.integers(0, n, (int(n_rep * 1.2), 2))
+    cand = cand[cand[:, 0] != cand[:, 1]]
+    ck = np.minimum(cand[:, 0], cand[:, 1]) * n + np.maximum(cand[:, 0], cand[:, 1])
+    ck = ck[~np.isin(ck, uniq)]
+    _, first = np.unique(ck, return_index=True)
+    ck = ck[np.sort(first)][:n_rep]
+    rep = np.stack([ck // n, ck % n], 1)
+    edges = np.concatenate([att, rep]).astype(np.int64)
+    w = np.concatenate([w_att, -np.ones(len(rep), np.float32)])
+    return edges, w
+
+
+def initial_iterate(seed, n=N_ITEMS, m=EMBED_DIM):
+    rng = np.random.default_rng(seed)
+    X0 = rng.standard_normal((n, m)).astype(np.float32)
+    return X0 - X0.mean(0)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows for k in range(4) if len(r) > 2 + k and r[2 + k] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(edges, w, X0, iters, warm=1):
+    """Time `iters` embed iterations of the same workload on the host cores.  Uses the UNMODIFIED
+    reference when baseline/_ref travelled with the repo (kind 'reference'), else the numpy oracle
+    port (kind 'port').  Returns dict(value=edges/s, iters_per_sec, cores, kind, sample)."""
+    import torch
+    from oracle.ref_loader import load_reference
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = load_reference()
+    p = len(edges)
+    if ref is not None:
+        f = ref.penalties.PushAndPull(torch.tensor(w), ref.penalties.Log1p, ref.penalties.Log)
+        mde = ref.MDE(X0.shape[0], X0.shape[1], torch.tensor(edges), f, ref.Centered(), device="cpu")
+        if warm:
+            mde.embed(X=torch.tensor(X0), max_iter=warm, eps=0.0)
+        t0 = time.perf_counter()
+        mde.embed(X=torch.tensor(X0), max_iter=iters, eps=0.0)
+        dt = time.perf_counter() - t0
+        done = mde.solve_stats.iterations
+        kind, threads = "reference", torch.get_num_threads()
+    else:
+        from oracle import mde_oracle as O
+        spec = O.FnSpec(O.P_LOG1P, w, (1.5, 0, 0), fn_rep=O.P_LOG, rep=(1.0, 0, 0))
+        t0 = time.perf_counter()
+        _, st = O.embed(X0, edges, spec, O.Centered(), eps=0.0, max_iter=iters, dtype=np.float32)
+        dt = time.perf_counter() - t0
+        done, kind, threads = st.iterations, "port", 1
+    ips = done / dt
+    return {"value": ips * p, "unit": "edges/s", "iters_per_sec": ips, "cores": threads, "kind": kind,
+            "sample": "%d embed iterations of the full workload (n=%d, p=%d) from the same X0" % (done, X0.shape[0], p),
+            "seconds": dt}
+
+
+def cuda_reference_run(edges, w, X0, iters, dev):
+    """The reference's own torch-CUDA path (device='cuda') on the same GPU: the denominator of the
+    north_star's '10x the reference's torch-CUDA embed() steps/sec'.  None when baseline/_ref is absent."""
+    import torch
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    if ref is None:
+        return None
+    try:
+        f = ref.penalties.PushAndPull(torch.tensor(w, device=dev), ref.penalties.Log1p, ref.penalties.Log)
+        mde = ref.MDE(X0.shape[0], X0.shape[1], torch.tensor(edges, device=dev), f, ref.Centered(), device=dev)
+        X0d = torch.tensor(X0, device=dev)
+        for _ in range(2):
+            mde.embed(X=X0d, max_iter=5, eps=0.0)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        mde.embed(X=X0d, max_iter=iters, eps=0.0)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        done = mde.solve_stats.iterations
+        return {"iters_per_sec": done / dt, "value": done / dt * len(edges), "unit": "edges/s", "iterations": done,
+                "final_average_distortion": float(mde.solve_stats.average_distortions[-1]),
+                "what": "unmodified reference, device='cuda', same edges/weights/X0, eps=0"}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-iters", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3)
+
+    workload = ("MNIST-shaped preserve_neighbors (synthetic): n=%d, m=%d, ~%d neighbours, PushAndPull(Log1p(1.5),"
+                " Log(1.0)), Centered" % (N_ITEMS, EMBED_DIM, K_NEIGHBORS))
+
+    # ---------------- reference arm: CPU implementation on the host cores ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        edges, w = c2_edges(0)
+        X0 = initial_iterate(0)
+        steps = min(K, 30)
+        r = cpu_reference_run(edges, w, X0, steps, warm=min(W, 2))
+        line = {"impl": "reference", "metric": "embed_edges_per_sec", "value": r["value"], "unit": "edges/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(W, 2), "ms_per_step": 1e3 / r["iters_per_sec"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "iters_per_sec": r["iters_per_sec"],
+                "config": {"workload": workload, "edges": int(len(edges)), "device": "cpu"},
+                "cpu_baseline": {"value": r["value"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- our arm ----------------
+    import torch
+    import pymde_b200 as pm
+    from pymde_b200 import _lib, dist as pdist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.init_process_group("nccl", device_id=dev)
+
+    edges, w = c2_edges(rank)  # weak scaling: every rank owns a C2-sized shard over the same items
+    p_local = len(edges)
+    X0 = initial_iterate(0)
+    if world > 1:
+        counts = torch.tensor([p_local], device=dev)
+        allc = [torch.zeros_like(counts) for _ in range(world)]
+        tdist.all_gather(allc, counts)
+        p_total = int(sum(int(c) for c in allc))
+    else:
+        p_total = p_local
+
+    wt = torch.tensor(w, device=dev)
+    f = pm.penalties.PushAndPull(wt, pm.penalties.Log1p, pm.penalties.Log)
+    mde = pm.MDE(N_ITEMS, EMBED_DIM, torch.tensor(edges, device=dev), f, pm.Centered(), device=dev)
+    if world > 1:
+        mde.__dict__["_dist"] = {"rank": rank, "world_size": world, "p_total": p_total,
+                                 "allreduce": pdist.make_allreduce(dev)}
+    lib = _lib.load()
+    X0d = torch.tensor(X0, device=dev)
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # -- device-resident throughput: W warm-up + K timed iterations of the solver loop -------
+    solver = mde._solver(mde.constraint, 10, K + W + 8)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    solver.begin(X0d, 0.0)
+    solver.run(W)
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = lib.mde_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    done, _ = solver.run(K)
+    ev1.record()
+    barrier()
+    launches = lib.mde_launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        ms = float(t.item())
+    iters_done = done - W
+    avg, res, pct, stp, fe = solver.stats(done)
+    clocks = sampler.stop() if sampler else None
+
+    # -- end to end through the public API with pinned HOST buffers ---------------------------
+    X0h = torch.tensor(X0).pin_memory()
+    out_h = torch.empty_like(X0h).pin_memory()
+    mde.embed(X=X0h, max_iter=W, eps=0.0)  # warm the API path
+    barrier()
+    t0 = time.perf_counter()
+    Xe = mde.embed(X=X0h, max_iter=K, eps=0.0)
+    out_h.copy_(Xe, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_iters = mde.solve_stats.iterations
+    h2d = X0h.numel() * 4
+    d2h = out_h.numel() * 4 + 4 * 8 * e2e_iters + 32 * int(mde.solve_stats.func_evals or e2e_iters)
+
+    if rank != 0:
+        return 0
+
+    # -- roofline of the fused distortion kernel: cold L2, one launch per timing -------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    lay = mde._layout()
+    grad = torch.zeros_like(X0d)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    times = []
+    st = torch.cuda.current_stream(dev).cuda_stream
+    for it in range(24):
+        flush.fill_(it & 0xFF)
+        grad.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(lib.mde_distortion(lay.handle, X0d.data_ptr(), EMBED_DIM, grad.data_ptr(), None, st))
+        b.record()
+        torch.cuda.synchronize(dev)
+        if it >= 4:
+            times.append(a.elapsed_time(b))
+    k_ms = float(np.mean(times))
+    b_alg = p_local * 12 + 2 * N_ITEMS * EMBED_DIM * 4 + 8
+    achieved = b_alg / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "distortion_small_kernel<2,0>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": b_alg, "kernel_ms_cold_l2": k_ms,
+                "timing": "CUDA events around one launch, 512 MB L2 flush before each, mean of 20"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        r = cpu_reference_run(edges, w, X0, args.cpu_iters, warm=1)
+        cpu_baseline = {"value": r["value"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+                        "sample": r["sample"], "iters_per_sec": r["iters_per_sec"]}
+
+    ref_cuda = None if args.no_cpu_baseline or world > 1 else cuda_reference_run(edges, w, X0, min(K, 100), dev)
+
+    ips = iters_done / (ms * 1e-3)
+    line = {
+        "metric": "embed_edges_per_sec", "value": ips * p_total, "unit": "edges/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / max(iters_done, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "edges_total": p_total, "edges_per_gpu": p_local,
+                   "parallelism": "edge-sharded x%d, X replicated, 1 all-reduce/eval" % world,
+                   "l2": "solver loop runs L2-warm (working set ~26 MB < 126 MB L2); roofline timed cold (flush)",
+                   "memory_size": 10},
+        "iters_per_sec": ips, "iterations_timed": iters_done, "func_evals_total": int(fe),
+        "final_average_distortion": float(avg[-1]) if len(avg) else None,
+        "e2e": {"value": e2e_iters / e2e_s * p_total, "unit": "edges/s", "iters_per_sec": e2e_iters / e2e_s,
+                "h2d_bytes_per_step": h2d / max(e2e_iters, 1), "d2h_bytes_per_step": d2h / max(e2e_iters, 1),
+                "what": "MDE.embed(X=pinned host X0, max_iter=K) + copy of the embedding to pinned host memory"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "reference_torch_cuda": ref_cuda,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

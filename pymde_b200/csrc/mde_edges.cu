@@ -1,0 +1,564 @@
+// mde_edges.cu -- edge layout + the fused average-distortion kernel (forward + backward).
+//
+// Replaces pymde/average_distortion.py:36-80 (gather X[lhs], X[rhs]; row norms; per-edge
+// penalty; mean; scatter-add of +-g*diff) and pymde/problem.py:246-307 (per-edge outputs).
+//
+// Data layout in HBM (one shard):
+//   src[p], dst[p]  int32   canonical (src < dst) endpoints, sorted by (class, src, dst)
+//                           class 0 = attractive/ordinary, 1 = repulsive (PushAndPull w < 0)
+//   par0[p]         fp32    weight | deviation, permuted alongside
+//   par1[p]         fp32    optional second array (WeightedQuadratic weights)
+//   perm[p]         int32   original position of sorted edge k (per-edge outputs only)
+// Algorithmic bytes per fused evaluation: p*(8+4k) + 2*n*m*4 + 8  (SURVEY section 8d).
+//
+// Kernel shapes
+//   m <= 4 : one thread per edge, 32 consecutive sorted edges per warp round; the lhs
+//            contributions (sorted => runs of equal src) are summed with a warp segmented
+//            reduction and issued as ONE vector red per run; rhs contributions go out as
+//            vector reds (REDG.E.ADD.F32x2/x4).
+//   m >= 5 : a group of G lanes (8/16/32) walks a contiguous slice of edges; the lhs row and
+//            its gradient accumulator stay in registers across a run.
+#include <cub/cub.cuh>
+#include <new>
+
+#include "mde_common.cuh"
+
+namespace mde {
+unsigned long long g_launch_count = 0;
+}
+
+using namespace mde;
+
+struct mde_edges {
+  int64_t p = 0, n = 0, p_total = 0;
+  int32_t *src = nullptr, *dst = nullptr, *perm = nullptr;
+  float *par0 = nullptr, *par1 = nullptr;
+  double* loss_partials = nullptr;  // [kMaxLossBlocks]
+  FnDev fn;
+  int has_par1 = 0;
+  int64_t nbytes = 0;
+};
+
+static constexpr int kMaxLossBlocks = 148 * 16;
+static constexpr int kSmallThreads = 256;
+static constexpr int kRounds = 4;  // 32-edge rounds per warp iteration
+
+// ------------------------------------------------------------------------------------------
+// layout build
+// ------------------------------------------------------------------------------------------
+__global__ void make_keys_kernel(const int64_t* __restrict__ edges, const float* __restrict__ par0,
+                                 int push_pull, int64_t p, uint64_t* __restrict__ keys,
+                                 int32_t* __restrict__ vals) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p) return;
+  int64_t i = edges[2 * k], j = edges[2 * k + 1];
+  uint64_t lo = (uint64_t)(i < j ? i : j), hi = (uint64_t)(i < j ? j : i);
+  uint64_t cls = (push_pull && !(par0[k] >= 0.0f)) ? 1ull : 0ull;
+  keys[k] = (cls << 63) | (lo << 32) | hi;  // n < 2^31
+  vals[k] = (int32_t)k;
+}
+
+__global__ void unpack_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
+                              const float* __restrict__ par0, const float* __restrict__ par1, int64_t p,
+                              int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                              float* __restrict__ p0, float* __restrict__ p1) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p) return;
+  uint64_t key = keys[k];
+  src[k] = (int32_t)((key >> 32) & 0x7fffffffu);
+  dst[k] = (int32_t)(key & 0xffffffffu);
+  int32_t o = vals[k];
+  p0[k] = par0[o];
+  if (par1) p1[k] = par1[o];
+}
+
+// ------------------------------------------------------------------------------------------
+// m <= 4: thread-per-edge kernel
+// ------------------------------------------------------------------------------------------
+template <int M> struct Row { float v[M]; };
+
+template <int M>
+__device__ __forceinline__ Row<M> load_row(const float* __restrict__ X, int r) {
+  Row<M> o;
+  if constexpr (M == 1) { o.v[0] = __ldg(X + r); }
+  else if constexpr (M == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(X) + r); o.v[0] = t.x; o.v[1] = t.y; }
+  else if constexpr (M == 4) { float4 t = __ldg(reinterpret_cast<const float4*>(X) + r); o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w; }
+  else {
+#pragma unroll
+    for (int c = 0; c < M; ++c) o.v[c] = __ldg(X + (int64_t)r * M + c);
+  }
+  return o;
+}
+
+template <int M>
+__device__ __forceinline__ void red_row(float* __restrict__ G, int r, const float (&v)[M], float sgn) {
+  if constexpr (M == 1) red_add(G + r, sgn * v[0]);
+  else if constexpr (M == 2) red_add_v2(G + 2 * (int64_t)r, sgn * v[0], sgn * v[1]);
+  else if constexpr (M == 4) red_add_v4(G + 4 * (int64_t)r, sgn * v[0], sgn * v[1], sgn * v[2], sgn * v[3]);
+  else {
+#pragma unroll
+    for (int c = 0; c < M; ++c) red_add(G + (int64_t)r * M + c, sgn * v[c]);
+  }
+}
+
+// MODE 0: fused value + gradient; 1: value only; 2: external per-edge g (gradient only)
+template <int M, int MODE>
+__global__ void __launch_bounds__(kSmallThreads)
+distortion_small_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                        const float* __restrict__ par0, const float* __restrict__ par1,
+                        const int32_t* __restrict__ perm, const float* __restrict__ gext,
+                        int64_t p, const float* __restrict__ X, float* __restrict__ grad,
+                        double* __restrict__ loss_partials, FnDev fn, float inv_p,
+                        const int* __restrict__ flag) {
+  if (flag != nullptr && *flag == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int64_t kPerWarp = 32 * kRounds;
+  double lsum = 0.0;
+
+  for (int64_t base = warp0 * kPerWarp; base < p; base += nwarps * kPerWarp) {
+    int s[kRounds], t[kRounds];
+    float a[kRounds], b[kRounds];
+    bool ok[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      int64_t k = base + r * 32 + lane;
+      ok[r] = k < p;
+      s[r] = ok[r] ? __ldg(src + k) : 0;
+      t[r] = ok[r] ? __ldg(dst + k) : 0;
+      if (MODE == 2) a[r] = ok[r] ? __ldg(gext + __ldg(perm + k)) : 0.0f;
+      else a[r] = ok[r] ? __ldg(par0 + k) : 0.0f;
+      b[r] = (MODE != 2 && par1 != nullptr && ok[r]) ? __ldg(par1 + k) : 0.0f;
+    }
+    Row<M> xi[kRounds], xj[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      xi[r] = load_row<M>(X, s[r]);
+      xj[r] = load_row<M>(X, t[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      float diff[M];
+      float d2 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < M; ++c) { diff[c] = xi[r].v[c] - xj[r].v[c]; d2 += diff[c] * diff[c]; }
+      float g;
+      if (MODE == 2) {
+        g = a[r];
+      } else {
+        float d = sqrtf(d2), f;
+        if (MODE == 0) edge_coeff(fn, d, a[r], b[r], inv_p, f, g);
+        else { edge_value(fn, d, a[r], b[r], f); g = 0.0f; }
+        if (ok[r]) lsum += (double)f;
+      }
+      if (MODE != 1) {
+        float v[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) v[c] = ok[r] ? g * diff[c] : 0.0f;
+        if (ok[r]) red_row<M>(grad, t[r], v, -1.0f);
+        // lhs: sorted => equal keys are adjacent lanes; segmented warp reduction
+        int key = ok[r] ? s[r] : (-1 - lane);
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          int k2 = __shfl_down_sync(kFull, key, off);
+          bool take = (lane + off < 32) && (k2 == key);
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+            float o = __shfl_down_sync(kFull, v[c], off);
+            if (take) v[c] += o;
+          }
+        }
+        int kprev = __shfl_up_sync(kFull, key, 1);
+        bool head = (lane == 0) || (kprev != key);
+        if (head && ok[r]) red_row<M>(grad, s[r], v, 1.0f);
+      }
+    }
+  }
+  if (MODE != 2) {
+    __shared__ double sm[32];
+    double v1[1] = {lsum};
+    block_sum<1>(v1, sm);
+    if (threadIdx.x == 0) loss_partials[blockIdx.x] = v1[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// m >= 5: group-per-edge kernel.  G lanes share one edge; lane l owns columns l, l+G, ...
+// (CPL of them).  VW = 4 treats the row as m/4 float4 columns.
+// ------------------------------------------------------------------------------------------
+template <int VW> struct Vec { float v[VW]; };
+
+template <int VW>
+__device__ __forceinline__ Vec<VW> ldv(const float* __restrict__ p) {
+  Vec<VW> o;
+  if constexpr (VW == 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w; }
+  else o.v[0] = __ldg(p);
+  return o;
+}
+template <int VW>
+__device__ __forceinline__ void redv(float* p, const Vec<VW>& x, float sgn) {
+  if constexpr (VW == 4) red_add_v4(p, sgn * x.v[0], sgn * x.v[1], sgn * x.v[2], sgn * x.v[3]);
+  else red_add(p, sgn * x.v[0]);
+}
+
+static constexpr int kWideThreads = 256;
+static constexpr int kWideSlice = 64;  // consecutive edges walked by one group
+
+template <int G, int CPL, int VW, int MODE>
+__global__ void __launch_bounds__(kWideThreads)
+distortion_wide_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                       const float* __restrict__ par0, const float* __restrict__ par1,
+                       const int32_t* __restrict__ perm, const float* __restrict__ gext,
+                       int64_t p, int m, const float* __restrict__ X, float* __restrict__ grad,
+                       double* __restrict__ loss_partials, FnDev fn, float inv_p,
+                       const int* __restrict__ flag) {
+  if (flag != nullptr && *flag == 0) return;
+  const int lg = threadIdx.x % G;
+  const int64_t group0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
+  const int mv = m / VW;  // columns in units of VW floats
+  double lsum = 0.0;
+
+  for (int64_t k0 = group0 * kWideSlice; k0 < p; k0 += ngroups * kWideSlice) {
+    int cur = -1;
+    Vec<VW> xi[CPL], acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int q = 0; q < VW; ++q) { xi[c].v[q] = 0.0f; acc[c].v[q] = 0.0f; }
+    // trip count is uniform across the warp (shuffles inside); work is predicated
+    for (int it = 0; it < kWideSlice; ++it) {
+      int64_t k = k0 + it;
+      bool ok = k < p;
+      int s = ok ? __ldg(src + k) : cur;
+      int t = ok ? __ldg(dst + k) : 0;
+      if (s != cur) {
+        if (cur >= 0 && MODE != 1) {
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) {
+            int col = lg + c * G;
+            if (col < mv) redv<VW>(grad + (int64_t)cur * m + col * VW, acc[c], 1.0f);
+          }
+        }
+        cur = s;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          int col = lg + c * G;
+#pragma unroll
+          for (int q = 0; q < VW; ++q) acc[c].v[q] = 0.0f;
+          if (col < mv) xi[c] = ldv<VW>(X + (int64_t)s * m + col * VW);
+        }
+      }
+      Vec<VW> diff[CPL];
+      float d2 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        int col = lg + c * G;
+#pragma unroll
+        for (int q = 0; q < VW; ++q) diff[c].v[q] = 0.0f;
+        if (ok && col < mv) {
+          Vec<VW> xj = ldv<VW>(X + (int64_t)t * m + col * VW);
+#pragma unroll
+          for (int q = 0; q < VW; ++q) { diff[c].v[q] = xi[c].v[q] - xj.v[q]; d2 += diff[c].v[q] * diff[c].v[q]; }
+        }
+      }
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) d2 += __shfl_xor_sync(kFull, d2, off);
+      float g, f = 0.0f;
+      if (MODE == 2) {
+        g = ok ? __ldg(gext + __ldg(perm + k)) : 0.0f;
+      } else {
+        float a = ok ? __ldg(par0 + k) : 1.0f;
+        float b = (ok && par1 != nullptr) ? __ldg(par1 + k) : 1.0f;
+        float d = sqrtf(d2);
+        if (MODE == 0) edge_coeff(fn, d, a, b, inv_p, f, g);
+        else { edge_value(fn, d, a, b, f); g = 0.0f; }
+        if (ok && lg == 0) lsum += (double)f;
+      }
+      if (MODE != 1 && ok) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          int col = lg + c * G;
+          if (col < mv) {
+            Vec<VW> v;
+#pragma unroll
+            for (int q = 0; q < VW; ++q) { v.v[q] = g * diff[c].v[q]; acc[c].v[q] += v.v[q]; }
+            redv<VW>(grad + (int64_t)t * m + col * VW, v, -1.0f);
+          }
+        }
+      }
+    }
+    if (cur >= 0 && MODE != 1) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        int col = lg + c * G;
+        if (col < mv) redv<VW>(grad + (int64_t)cur * m + col * VW, acc[c], 1.0f);
+      }
+    }
+  }
+  if (MODE != 2) {
+    __shared__ double sm[32];
+    double v1[1] = {lsum};
+    block_sum<1>(v1, sm);
+    if (threadIdx.x == 0) loss_partials[blockIdx.x] = v1[0];
+  }
+}
+
+// sum of per-block partials, added to *out (single block; fixed order => deterministic)
+__global__ void add_partials_kernel(const double* __restrict__ partials, int nblocks, double* out) {
+  __shared__ double sm[32];
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v[0] += partials[i];
+  block_sum<1>(v, sm);
+  if (threadIdx.x == 0) out[0] += v[0];
+}
+
+// per-edge outputs in the caller's order
+template <int MFIX>
+__global__ void edge_outputs_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                    const float* __restrict__ par0, const float* __restrict__ par1,
+                                    const int32_t* __restrict__ perm, int64_t p, int m,
+                                    const float* __restrict__ X, float* __restrict__ distances,
+                                    float* __restrict__ distortions, FnDev fn) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p) return;
+  int s = src[k], t = dst[k];
+  float d2 = 0.0f;
+  for (int c = 0; c < m; ++c) {
+    float df = __ldg(X + (int64_t)s * m + c) - __ldg(X + (int64_t)t * m + c);
+    d2 += df * df;
+  }
+  float d = sqrtf(d2);
+  int o = perm[k];
+  if (distances) distances[o] = d;
+  if (distortions) {
+    float f;
+    edge_value(fn, d, par0[k], par1 ? par1[k] : 0.0f, f);
+    distortions[o] = f;
+  }
+}
+
+__global__ void function_eval_kernel(FnDev fn, const float* __restrict__ par0, int64_t par0_len,
+                                     const float* __restrict__ par1, const float* __restrict__ dist,
+                                     int64_t p, float* __restrict__ f_out, float* __restrict__ fp_out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p) return;
+  float a = par0[par0_len == 1 ? 0 : k];
+  float b = par1 ? par1[k] : 0.0f;
+  float d = dist[k];
+  const bool rep = fn.push_pull && !(a >= 0.0f);
+  float f, fp;
+  if (rep) eval_fn(fn.fn_rep, fn.r0, fn.r1, d, a, b, f, fp);
+  else eval_fn(fn.fn_att, fn.a0, fn.a1, d, a, b, f, fp);
+  if (f_out) f_out[k] = f;
+  if (fp_out) fp_out[k] = fp;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+namespace mde {
+
+int loss_blocks_small(int64_t p) {
+  int64_t per_block = (int64_t)(kSmallThreads / 32) * 32 * kRounds;
+  int64_t nb = (p + per_block - 1) / per_block;
+  if (nb < 1) nb = 1;
+  if (nb > kNumSMs * 8) nb = kNumSMs * 8;
+  return (int)nb;
+}
+
+int loss_blocks_wide(int64_t p, int G) {
+  int64_t groups_per_block = kWideThreads / G;
+  int64_t per_block = groups_per_block * kWideSlice;
+  int64_t nb = (p + per_block - 1) / per_block;
+  if (nb < 1) nb = 1;
+  if (nb > kNumSMs * 8) nb = kNumSMs * 8;
+  return (int)nb;
+}
+
+template <int MODE>
+int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, const float* gext,
+                      int* nblocks_out, const int* flag, cudaStream_t st) {
+  const float inv_p = 1.0f / (float)e->p_total;
+  const int64_t p = e->p;
+  int nb;
+#define SMALL(MM)                                                                                     \
+  nb = loss_blocks_small(p);                                                                          \
+  distortion_small_kernel<MM, MODE><<<nb, kSmallThreads, 0, st>>>(                                    \
+      e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
+      e->loss_partials, e->fn, inv_p, flag)
+#define WIDE(GG, CC, VV)                                                                              \
+  nb = loss_blocks_wide(p, GG);                                                                       \
+  distortion_wide_kernel<GG, CC, VV, MODE><<<nb, kWideThreads, 0, st>>>(                              \
+      e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, m, X, grad,        \
+      e->loss_partials, e->fn, inv_p, flag)
+  if (m == 1) { SMALL(1); }
+  else if (m == 2) { SMALL(2); }
+  else if (m == 3) { SMALL(3); }
+  else if (m == 4) { SMALL(4); }
+  else if (m % 4 == 0) {
+    int mv = m / 4;
+    if (mv <= 8) { WIDE(8, 1, 4); }
+    else if (mv <= 16) { WIDE(16, 1, 4); }
+    else if (mv <= 32) { WIDE(32, 1, 4); }
+    else if (mv <= 64) { WIDE(32, 2, 4); }
+    else if (mv <= 128) { WIDE(32, 4, 4); }
+    else if (mv <= 256) { WIDE(32, 8, 4); }
+    else return MDE_E_UNSUPPORTED;
+  } else {
+    if (m <= 8) { WIDE(8, 1, 1); }
+    else if (m <= 16) { WIDE(16, 1, 1); }
+    else if (m <= 32) { WIDE(32, 1, 1); }
+    else if (m <= 64) { WIDE(32, 2, 1); }
+    else if (m <= 128) { WIDE(32, 4, 1); }
+    else if (m <= 256) { WIDE(32, 8, 1); }
+    else if (m <= 512) { WIDE(32, 16, 1); }
+    else return MDE_E_UNSUPPORTED;
+  }
+#undef SMALL
+#undef WIDE
+  MDE_LAUNCH_CHECK();
+  if (nblocks_out) *nblocks_out = nb;
+  return 0;
+}
+
+// used by the solver: fused launch leaving per-block loss partials in e->loss_partials
+int distortion_fused(const mde_edges* e, const float* X, int m, float* grad, int* nblocks, cudaStream_t st) {
+  return launch_distortion<0>(e, X, m, grad, nullptr, nblocks, nullptr, st);
+}
+int distortion_fused_flag(const mde_edges* e, const float* X, int m, float* grad, int* nblocks,
+                          const int* flag, cudaStream_t st) {
+  return launch_distortion<0>(e, X, m, grad, nullptr, nblocks, flag, st);
+}
+int64_t edges_p_total(const mde_edges* e) { return e->p_total; }
+const double* loss_partials_ptr(const mde_edges* e) { return e->loss_partials; }
+int64_t edges_n(const mde_edges* e) { return e->n; }
+
+}  // namespace mde
+
+extern "C" {
+
+int mde_abi_version(void) { return MDE_ABI_VERSION; }
+
+uint64_t mde_launch_count(void) { return (uint64_t)mde::g_launch_count; }
+
+const char* mde_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case MDE_E_INVALID: return "mde: invalid argument";
+    case MDE_E_UNSUPPORTED: return "mde: unsupported configuration";
+    case MDE_E_NAN: return "mde: function or gradient evaluation returned NaN/Inf";
+    case MDE_E_ALLOC: return "mde: allocation failed";
+  }
+  return "mde: unknown error";
+}
+
+int mde_edges_create(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t n_items,
+                     const float* par0, const float* par1, const mde_fn_t* fn, int64_t p_total,
+                     void* stream) {
+  if (!out || !edges || !par0 || !fn || p <= 0 || n_items <= 0 || p >= (1ll << 31) ||
+      n_items >= (1ll << 31) || p_total < p)
+    return MDE_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  mde_edges* e = new (std::nothrow) mde_edges();
+  if (!e) return MDE_E_ALLOC;
+  e->p = p; e->n = n_items; e->p_total = p_total; e->fn = to_dev(*fn); e->has_par1 = par1 != nullptr;
+
+  uint64_t *keys_in = nullptr, *keys_out = nullptr;
+  int32_t *vals_in = nullptr, *vals_out = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  int rc = 0;
+#define TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
+  TRY(cudaMalloc(&keys_in, sizeof(uint64_t) * p));
+  TRY(cudaMalloc(&keys_out, sizeof(uint64_t) * p));
+  TRY(cudaMalloc(&vals_in, sizeof(int32_t) * p));
+  TRY(cudaMalloc(&vals_out, sizeof(int32_t) * p));
+  TRY(cudaMalloc(&e->src, sizeof(int32_t) * p));
+  TRY(cudaMalloc(&e->dst, sizeof(int32_t) * p));
+  TRY(cudaMalloc(&e->par0, sizeof(float) * p));
+  if (par1) TRY(cudaMalloc(&e->par1, sizeof(float) * p));
+  TRY(cudaMalloc(&e->loss_partials, sizeof(double) * kMaxLossBlocks));
+  e->nbytes = p * (4 + 4 + 4 + 4 + (par1 ? 4 : 0)) + 8 * kMaxLossBlocks;
+  {
+    int tb = 256;
+    int nb = ceil_div_i64(p, tb);
+    make_keys_kernel<<<nb, tb, 0, st>>>(edges, par0, fn->push_pull, p, keys_in, vals_in);
+    ++g_launch_count;
+    TRY(cudaPeekAtLastError());
+    TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p, 0, 64, st));
+    TRY(cudaMalloc(&tmp, tmp_bytes));
+    TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p, 0, 64, st));
+    unpack_kernel<<<nb, tb, 0, st>>>(keys_out, vals_out, par0, par1, p, e->src, e->dst, e->par0, e->par1);
+    ++g_launch_count;
+    TRY(cudaPeekAtLastError());
+    TRY(cudaStreamSynchronize(st));
+  }
+  e->perm = vals_out;  // keep: original position of each sorted edge
+  vals_out = nullptr;
+  cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(tmp);
+  *out = e;
+  return 0;
+fail:
+  cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(vals_out); cudaFree(tmp);
+  mde_edges_destroy(e);
+  return rc;
+#undef TRY
+}
+
+int mde_edges_destroy(mde_edges_t* e) {
+  if (!e) return 0;
+  cudaFree(e->src); cudaFree(e->dst); cudaFree(e->perm); cudaFree(e->par0); cudaFree(e->par1);
+  cudaFree(e->loss_partials);
+  delete e;
+  return 0;
+}
+
+int64_t mde_edges_count(const mde_edges_t* e) { return e ? e->p : 0; }
+int64_t mde_edges_nbytes(const mde_edges_t* e) { return e ? e->nbytes : 0; }
+
+int mde_distortion(const mde_edges_t* e, const float* X, int m, float* grad, double* loss_sum,
+                   void* stream) {
+  if (!e || !X || m < 1) return MDE_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int nb = 0, rc;
+  if (grad) rc = launch_distortion<0>(e, X, m, grad, nullptr, &nb, nullptr, st);
+  else rc = launch_distortion<1>(e, X, m, nullptr, nullptr, &nb, nullptr, st);
+  if (rc) return rc;
+  if (loss_sum) {  // NULL: leave the per-block partials (kernel-only timing)
+    add_partials_kernel<<<1, 256, 0, st>>>(e->loss_partials, nb, loss_sum);
+    MDE_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int mde_function_eval(const mde_fn_t* fn, const float* par0, int64_t par0_len, const float* par1,
+                      const float* distances, int64_t p, float* f, float* fprime, void* stream) {
+  if (!fn || !par0 || !distances || p < 0 || (par0_len != 1 && par0_len != p)) return MDE_E_INVALID;
+  if (p == 0) return 0;
+  int tb = 256, nb = ceil_div_i64(p, tb);
+  function_eval_kernel<<<nb, tb, 0, (cudaStream_t)stream>>>(to_dev(*fn), par0, par0_len, par1, distances, p, f, fprime);
+  MDE_LAUNCH_CHECK();
+  return 0;
+}
+
+int mde_scatter_external(const mde_edges_t* e, const float* X, int m, const float* g, float* grad,
+                         void* stream) {
+  if (!e || !X || !g || !grad || m < 1) return MDE_E_INVALID;
+  return launch_distortion<2>(e, X, m, grad, g, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int mde_edge_outputs(const mde_edges_t* e, const float* X, int m, float* distances, float* distortions,
+                     void* stream) {
+  if (!e || !X || m < 1) return MDE_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int tb = 256, nb = ceil_div_i64(e->p, tb);
+  edge_outputs_kernel<0><<<nb, tb, 0, st>>>(e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr,
+                                            e->perm, e->p, m, X, distances, distortions, e->fn);
+  MDE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

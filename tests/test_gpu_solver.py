@@ -1,0 +1,170 @@
+"""GPU parity tests of the device-resident projected L-BFGS (mde_solver_*) through MDE.embed:
+against the reference's own embed() trajectories (tests/golden/trajectories.npz) and the numpy
+oracle, plus size-independent invariants of the constraint sets."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mde_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TRAJ = ["quad_std", "pp_cen", "pp_std", "cycle_abs", "huber_std", "docs5"]
+
+
+def build(pm, key, g):
+    par0 = torch.tensor(g[key + "/par0"], device="cuda")
+    pen, los = pm.penalties, pm.losses
+    f, c = {
+        "quad_std": (lambda: pen.Quadratic(par0), pm.Standardized()),
+        "pp_cen": (lambda: pen.PushAndPull(par0, pen.Log1p, pen.Log), pm.Centered()),
+        "pp_std": (lambda: pen.PushAndPull(par0, pen.Log1p, pen.Log), pm.Standardized()),
+        "cycle_abs": (lambda: los.Absolute(par0), pm.Centered()),
+        "huber_std": (lambda: los.Huber(par0, 0.5), pm.Standardized()),
+        "docs5": (lambda: pen.Quadratic(par0), pm.Standardized()),
+    }[key]
+    X0 = torch.tensor(g[key + "/X0"], device="cuda")
+    n, m = X0.shape
+    return pm.MDE(n, m, torch.tensor(g[key + "/edges"], device="cuda"), f(), c), X0
+
+
+@pytest.mark.parametrize("key", TRAJ)
+def test_embed_follows_reference_trajectory(golden, key):
+    import pymde_b200 as pm
+    g = golden["trajectories"]
+    mde, X0 = build(pm, key, g)
+    X = mde.embed(X=X0, max_iter=int(g[key + "/max_iter"]), eps=float(g[key + "/eps"]))
+    st = mde.solve_stats
+    ref = g[key + "/average_distortions"]
+    # iteration 0 is a plain evaluation at X0: per-evaluation parity, 1e-5 relative (north_star)
+    np.testing.assert_allclose(st.average_distortions[0], ref[0], rtol=1e-5)
+    np.testing.assert_allclose(st.residual_norms[0], g[key + "/residual_norms"][0], rtol=1e-4)
+    # the first iterations track the reference within fp32 summation-order noise
+    k = min(5, len(ref), st.iterations)
+    np.testing.assert_allclose(st.average_distortions[:k], ref[:k], rtol=1e-3)
+    np.testing.assert_allclose(st.step_size_percents[0], g[key + "/step_size_percents"][0], rtol=5e-3)
+    final = mde.average_distortion(X).item()
+    if key in ("quad_std", "docs5"):  # problems that converge: final value within 1e-5 relative
+        np.testing.assert_allclose(final, g[key + "/final_value"], rtol=1e-5)
+    else:  # non-converged after 40 iterations: within the reference's own run-to-run spread
+        np.testing.assert_allclose(final, g[key + "/final_value"], rtol=1e-2)
+    # value reported == loss at the start of the last iteration
+    assert mde.value == st.average_distortions[-1]
+    assert X.data_ptr() == mde.X.data_ptr()
+
+
+@pytest.mark.parametrize("key", TRAJ)
+def test_embed_matches_fp32_oracle(golden, key):
+    """Same inputs through the numpy restatement in fp32: iteration counts and early losses agree."""
+    import pymde_b200 as pm
+    from tests.test_oracle_golden import _spec_for_traj
+    g = golden["trajectories"]
+    mde, X0 = build(pm, key, g)
+    mde.embed(X=X0, max_iter=12, eps=float(g[key + "/eps"]))
+    spec, cons = _spec_for_traj(key, g[key + "/par0"])
+    _, st = O.embed(g[key + "/X0"], g[key + "/edges"], spec, cons, eps=float(g[key + "/eps"]), max_iter=12,
+                    dtype=np.float32)
+    k = min(4, st.iterations, mde.solve_stats.iterations)
+    np.testing.assert_allclose(mde.solve_stats.average_distortions[:k], st.average_distortions[:k], rtol=1e-3)
+    np.testing.assert_allclose(mde.solve_stats.residual_norms[:k], st.residual_norms[:k], rtol=2e-2, atol=1e-6)
+
+
+def _knn_problem(pm, n, k, m, seed, constraint):
+    rng = np.random.default_rng(seed)
+    i = np.repeat(np.arange(n), k)
+    j = (i + rng.integers(1, 50, n * k)) % n
+    att = np.unique(np.sort(np.stack([i, j], 1), axis=1), axis=0)
+    rep = rng.integers(0, n, (len(att), 2))
+    rep = rep[rep[:, 0] != rep[:, 1]]
+    rep = np.unique(np.sort(rep, axis=1), axis=0)
+    # drop repulsive pairs that are also attractive
+    key = lambda e: e[:, 0].astype(np.int64) * n + e[:, 1]
+    rep = rep[~np.isin(key(rep), key(att))]
+    edges = np.concatenate([att, rep]).astype(np.int64)
+    w = np.concatenate([np.ones(len(att)), -np.ones(len(rep))]).astype(np.float32)
+    f = pm.penalties.PushAndPull(torch.tensor(w, device="cuda"), pm.penalties.Log1p, pm.penalties.Log)
+    return pm.MDE(n, m, torch.tensor(edges, device="cuda"), f, constraint), edges, w
+
+
+@pytest.mark.parametrize("cname", ["centered", "standardized"])
+def test_embed_invariants_medium(cname):
+    import pymde_b200 as pm
+    cons = pm.Centered() if cname == "centered" else pm.Standardized()
+    n, m = 20000, 2
+    mde, edges, w = _knn_problem(pm, n, 8, m, 1, cons)
+    pm.seed(0)
+    X = mde.embed(max_iter=60, eps=1e-6)
+    st = mde.solve_stats
+    assert st.iterations == 60 and len(st.residual_norms) == 60 and len(st.step_size_percents) == 60
+    assert torch.isfinite(X).all()
+    assert st.average_distortions[-1] < st.average_distortions[0]
+    # line search accepts only decreasing losses (Armijo) -> monotone sequence
+    assert all(b <= a + 1e-6 * abs(a) for a, b in zip(st.average_distortions, st.average_distortions[1:]))
+    np.testing.assert_allclose(X.mean(0).cpu().numpy(), 0, atol=1e-5)
+    if cname == "standardized":
+        X64 = X.double()
+        np.testing.assert_allclose((X64.T @ X64 / n).cpu().numpy(), np.eye(m), atol=1e-4)
+    # final loss agrees with the oracle's evaluation of the returned embedding
+    spec = O.FnSpec(O.P_LOG1P, w, (1.5, 0, 0), fn_rep=O.P_LOG, rep=(1.0, 0, 0))
+    v_ref, _ = O.average_distortion(X.cpu().double().numpy(), edges, spec, False)
+    np.testing.assert_allclose(mde.average_distortion(X).item(), v_ref, rtol=1e-5)
+    assert st.func_evals >= st.iterations
+
+
+def test_converges_and_stops_early():
+    import pymde_b200 as pm
+    n = 200
+    edges = pm.all_edges(n)
+    mde = pm.MDE(n, 2, edges.cuda(), pm.penalties.Quadratic(torch.ones(edges.shape[0])), pm.Standardized())
+    pm.seed(0)
+    mde.embed(max_iter=500, eps=1e-4)
+    assert mde.solve_stats.iterations < 500
+    assert mde.residual_norm <= 1e-4
+    # all-pairs unit-weight quadratic + standardized: every standardized X has the same value 2*m*n/(n-1)
+    np.testing.assert_allclose(mde.average_distortion(mde.X).item(), 2.0 * 2 * n / (n - 1), rtol=1e-4)
+
+
+def test_anchored_constraint_keeps_anchors():
+    import pymde_b200 as pm
+    rng = np.random.default_rng(3)
+    n, m = 300, 2
+    mde0, edges, w = _knn_problem(pm, n, 5, m, 2, pm.Centered())
+    anchors = torch.tensor([0, 5, 17], device="cuda")
+    values = torch.tensor(rng.standard_normal((3, m)).astype(np.float32), device="cuda")
+    f = pm.penalties.PushAndPull(torch.tensor(w, device="cuda"), pm.penalties.Log1p, pm.penalties.Log)
+    mde = pm.MDE(n, m, torch.tensor(edges, device="cuda"), f, pm.Anchored(anchors, values))
+    pm.seed(0)
+    X = mde.embed(max_iter=30)
+    np.testing.assert_allclose(X[anchors].cpu().numpy(), values.cpu().numpy(), atol=0)
+    assert mde.solve_stats.average_distortions[-1] < mde.solve_stats.average_distortions[0]
+
+
+def test_custom_constraint_and_callable_use_generic_solver():
+    import pymde_b200 as pm
+
+    class Sphere(pm.constraints.Constraint):
+        def name(self):
+            return "sphere"
+
+        def initialization(self, n_items, embedding_dim, device=None):
+            X = torch.randn((int(n_items), int(embedding_dim)), device="cuda")
+            return X / X.norm(dim=1)[:, None]
+
+        def project_onto_constraint(self, Z, inplace=True):
+            return Z.div_(Z.norm(dim=1)[:, None]) if inplace else Z / Z.norm(dim=1)[:, None]
+
+        def project_onto_tangent_space(self, X, Z, inplace=True):
+            dual = (Z * X).sum(1)
+            return Z.sub_(dual[:, None] * X) if inplace else Z - dual[:, None] * X
+
+    n, m = 400, 3
+    mde0, edges, w = _knn_problem(pm, n, 5, m, 4, pm.Centered())
+    wt = torch.tensor(np.abs(w), device="cuda")
+    mde = pm.MDE(n, m, torch.tensor(edges, device="cuda"), pm.penalties.Quadratic(wt), Sphere())
+    pm.seed(0)
+    X = mde.embed(max_iter=25)
+    np.testing.assert_allclose(X.norm(dim=1).cpu().numpy(), 1.0, atol=1e-5)
+    assert mde.solve_stats.average_distortions[-1] < mde.solve_stats.average_distortions[0]
+    mde2 = pm.MDE(n, m, torch.tensor(edges, device="cuda"), lambda d: wt * d.pow(2), pm.Centered())
+    mde2.embed(max_iter=10)
+    assert mde2.solve_stats.average_distortions[-1] < mde2.solve_stats.average_distortions[0]
