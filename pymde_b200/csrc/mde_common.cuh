@@ -60,103 +60,142 @@ __device__ __forceinline__ void pow_pair(float d, float e, float& de, float& dem
   else { de = powf(d, e); dem1 = powf(d, e - 1.0f); }
 }
 
-// f(d) and f'(d) for one function id.  a = weight | deviation, b = second per-edge array.
-__device__ __forceinline__ void eval_fn(int fn, float s0, float s1, float d, float a, float b,
-                                        float& f, float& fp) {
-  switch (fn) {
-    case MDE_FN_P_LINEAR: f = a * d; fp = a; break;
-    case MDE_FN_P_QUADRATIC: f = a * d * d; fp = 2.0f * a * d; break;
-    case MDE_FN_P_CUBIC: f = a * d * d * d; fp = 3.0f * a * d * d; break;
-    case MDE_FN_P_POWER: {
-      float de, dem1; pow_pair(d, s0, de, dem1);
-      f = a * de; fp = a * s0 * dem1; break;
-    }
-    case MDE_FN_P_HUBER: {
-      if (d < s0) { f = a * 0.5f * d * d; fp = a * d; }
+// f(d) and f'(d) for one function id known at COMPILE time.  a = weight | deviation,
+// b = second per-edge array (WeightedQuadratic weights).
+template <int FN>
+__device__ __forceinline__ void eval_fn_t(float s0, float s1, float d, float a, float b, float& f, float& fp) {
+  if constexpr (FN == MDE_FN_P_LINEAR) {
+    f = a * d; fp = a;
+  }
+  else if constexpr (FN == MDE_FN_P_QUADRATIC) {
+    f = a * d * d; fp = 2.0f * a * d;
+  }
+  else if constexpr (FN == MDE_FN_P_CUBIC) {
+    f = a * d * d * d; fp = 3.0f * a * d * d;
+  }
+  else if constexpr (FN == MDE_FN_P_POWER) {
+    float de, dem1; pow_pair(d, s0, de, dem1);
+      f = a * de; fp = a * s0 * dem1;
+  }
+  else if constexpr (FN == MDE_FN_P_HUBER) {
+    if (d < s0) { f = a * 0.5f * d * d; fp = a * d; }
       else { f = a * s0 * (d - 0.5f * s0); fp = a * s0; }
-      break;
-    }
-    case MDE_FN_P_LOGISTIC: {
-      float z = s1 * (d - s0);
+  }
+  else if constexpr (FN == MDE_FN_P_LOGISTIC) {
+    float z = s1 * (d - s0);
       f = a * (fmaxf(z, 0.0f) + log1pf(expf(-fabsf(z))));
       fp = a * s1 / (1.0f + expf(-z));
-      break;
-    }
-    case MDE_FN_P_LOG1P: {
-      float de, dem1; pow_pair(d, s0, de, dem1);
-      f = a * log1pf(de); fp = a * s0 * dem1 / (1.0f + de); break;
-    }
-    case MDE_FN_P_LOG: {
-      float de, dem1; pow_pair(d, s0, de, dem1);
-      f = a * logf(-expm1f(-de)); fp = a * s0 * dem1 / expm1f(de); break;
-    }
-    case MDE_FN_P_INVPOWER: {
-      float de, dem1; pow_pair(d, s0, de, dem1);
+  }
+  else if constexpr (FN == MDE_FN_P_LOG1P) {
+    float de, dem1; pow_pair(d, s0, de, dem1);
+      f = a * log1pf(de); fp = a * s0 * dem1 / (1.0f + de);
+  }
+  else if constexpr (FN == MDE_FN_P_LOG) {
+    float de, dem1; pow_pair(d, s0, de, dem1);
+      f = a * logf(-expm1f(-de)); fp = a * s0 * dem1 / expm1f(de);
+  }
+  else if constexpr (FN == MDE_FN_P_INVPOWER) {
+    float de, dem1; pow_pair(d, s0, de, dem1);
       float aw = fabsf(a);
-      f = aw / de; fp = -aw * s0 / (de * d); break;
-    }
-    case MDE_FN_P_LOGRATIO: {
-      float de, dem1; pow_pair(d, s0, de, dem1);
-      f = a * logf(de / (1.0f + de)); fp = a * s0 / (d * (1.0f + de)); break;
-    }
-    case MDE_FN_L_ABSOLUTE: f = fabsf(a - d); fp = signf(d - a); break;
-    case MDE_FN_L_QUADRATIC: { float r = a - d; f = r * r; fp = 2.0f * (d - a); break; }
-    case MDE_FN_L_WEIGHTED_QUADRATIC: { float r = a - d; f = b * r * r; fp = 2.0f * b * (d - a); break; }
-    case MDE_FN_L_HUBER: {
-      float r = fabsf(a - d);
+      f = aw / de; fp = -aw * s0 / (de * d);
+  }
+  else if constexpr (FN == MDE_FN_P_LOGRATIO) {
+    float de, dem1; pow_pair(d, s0, de, dem1);
+      f = a * logf(de / (1.0f + de)); fp = a * s0 / (d * (1.0f + de));
+  }
+  else if constexpr (FN == MDE_FN_L_ABSOLUTE) {
+    f = fabsf(a - d); fp = signf(d - a);
+  }
+  else if constexpr (FN == MDE_FN_L_QUADRATIC) {
+    float r = a - d; f = r * r; fp = 2.0f * (d - a);
+  }
+  else if constexpr (FN == MDE_FN_L_WEIGHTED_QUADRATIC) {
+    float r = a - d; f = b * r * r; fp = 2.0f * b * (d - a);
+  }
+  else if constexpr (FN == MDE_FN_L_HUBER) {
+    float r = fabsf(a - d);
       if (r < s0) { f = r * r; fp = 2.0f * (d - a); }
       else { f = s0 * (2.0f * r - s0); fp = 2.0f * s0 * signf(d - a); }
-      break;
-    }
-    case MDE_FN_L_CUBIC: { float r = fabsf(a - d); f = r * r * r; fp = 3.0f * r * r * signf(d - a); break; }
-    case MDE_FN_L_POWER: {
-      float r = fabsf(a - d); float re, rem1; pow_pair(r, s0, re, rem1);
-      f = re; fp = s0 * rem1 * signf(d - a); break;
-    }
-    case MDE_FN_L_LOGISTIC: {  // naive log(1 + exp(r)) as written in losses.py:184-186
+  }
+  else if constexpr (FN == MDE_FN_L_CUBIC) {
+    float r = fabsf(a - d); f = r * r * r; fp = 3.0f * r * r * signf(d - a);
+  }
+  else if constexpr (FN == MDE_FN_L_POWER) {
+    float r = fabsf(a - d); float re, rem1; pow_pair(r, s0, re, rem1);
+      f = re; fp = s0 * rem1 * signf(d - a);
+  }
+  else if constexpr (FN == MDE_FN_L_LOGISTIC) {
+    // naive log(1 + exp(r)) as written in losses.py:184-186
       float r = fabsf(a - d); float er = expf(r);
-      f = logf(1.0f + er); fp = er / (1.0f + er) * signf(d - a); break;
-    }
-    case MDE_FN_L_FRACTIONAL: {
-      float u = a / d, v = d / a;
+      f = logf(1.0f + er); fp = er / (1.0f + er) * signf(d - a);
+  }
+  else if constexpr (FN == MDE_FN_L_FRACTIONAL) {
+    float u = a / d, v = d / a;
       f = fmaxf(u, v) - 1.0f;
       float du = -a / (d * d), dv = 1.0f / a;
       fp = (v > u) ? dv : ((u > v) ? du : 0.5f * (du + dv));
-      break;
-    }
-    case MDE_FN_L_SOFT_FRACTIONAL: {
-      float u = s0 * a / d, v = s0 * d / a;
+  }
+  else if constexpr (FN == MDE_FN_L_SOFT_FRACTIONAL) {
+    float u = s0 * a / d, v = s0 * d / a;
       float mx = fmaxf(u, v);
       float lse = isinf(mx) ? mx : mx + logf(expf(u - mx) + expf(v - mx));
       float inv_gamma = 1.0f / s0;
       f = inv_gamma * (lse - (0.69314718f + s0));
       float pu = expf(u - lse), pv = expf(v - lse);
       fp = (inv_gamma * s0) * (pu * (-a / (d * d)) + pv * (1.0f / a));
-      break;
-    }
+  }
+  else { f = 0.0f; fp = 0.0f; }
+}
+
+// Run-time function id: ONE out-of-line copy of the whole table (keeps the generic kernels small).
+static __device__ __noinline__ float2 eval_fn_rt(int fn, float s0, float s1, float d, float a, float b) {
+  float f, fp;  // returned by value: references into a non-inlined call would live in local memory
+  switch (fn) {
+#define MDE_CASE(X) case X: eval_fn_t<X>(s0, s1, d, a, b, f, fp); break;
+    MDE_CASE(MDE_FN_P_LINEAR) MDE_CASE(MDE_FN_P_QUADRATIC) MDE_CASE(MDE_FN_P_CUBIC) MDE_CASE(MDE_FN_P_POWER)
+    MDE_CASE(MDE_FN_P_HUBER) MDE_CASE(MDE_FN_P_LOGISTIC) MDE_CASE(MDE_FN_P_LOG1P) MDE_CASE(MDE_FN_P_LOG)
+    MDE_CASE(MDE_FN_P_INVPOWER) MDE_CASE(MDE_FN_P_LOGRATIO) MDE_CASE(MDE_FN_L_ABSOLUTE) MDE_CASE(MDE_FN_L_QUADRATIC)
+    MDE_CASE(MDE_FN_L_WEIGHTED_QUADRATIC) MDE_CASE(MDE_FN_L_HUBER) MDE_CASE(MDE_FN_L_CUBIC) MDE_CASE(MDE_FN_L_POWER)
+    MDE_CASE(MDE_FN_L_LOGISTIC) MDE_CASE(MDE_FN_L_FRACTIONAL) MDE_CASE(MDE_FN_L_SOFT_FRACTIONAL)
+#undef MDE_CASE
     default: f = 0.0f; fp = 0.0f; break;
+  }
+  return make_float2(f, fp);
+}
+
+// f_k(d) and f'_k(d) of edge k.  FA/FR >= 0: function ids fixed at compile time (hot combinations);
+// FA < 0: run-time table.  PushAndPull picks attractive/repulsive by weight sign (penalties.py:390).
+template <int FA, int FR>
+__device__ __forceinline__ void edge_f_fp(const FnDev& fn, float d, float a, float b, float& f, float& fp) {
+  if constexpr (FA < 0) {
+    const bool rep = fn.push_pull && !(a >= 0.0f);
+    const float2 r = rep ? eval_fn_rt(fn.fn_rep, fn.r0, fn.r1, d, a, b) : eval_fn_rt(fn.fn_att, fn.a0, fn.a1, d, a, b);
+    f = r.x; fp = r.y;
+  } else if constexpr (FA == FR) {
+    eval_fn_t<FA>(fn.a0, fn.a1, d, a, b, f, fp);
+  } else {
+    if (!(a >= 0.0f)) eval_fn_t<FR>(fn.r0, fn.r1, d, a, b, f, fp);
+    else eval_fn_t<FA>(fn.a0, fn.a1, d, a, b, f, fp);
   }
 }
 
 // Per-edge distortion f_k(d) and gradient coefficient g_k = f'_k(d) / (p d), with the
 // reference's guard: non-finite g -> 1.0 (pymde/average_distortion.py:55-62; it only fires
 // when d = 0, where the difference vector is 0 too).
+template <int FA, int FR>
 __device__ __forceinline__ void edge_coeff(const FnDev& fn, float d, float a, float b, float inv_p,
                                            float& f, float& g) {
-  const bool rep = fn.push_pull && !(a >= 0.0f);  // penalties.py:390  (w >= 0 -> attractive)
   float fp;
-  if (rep) eval_fn(fn.fn_rep, fn.r0, fn.r1, d, a, b, f, fp);
-  else eval_fn(fn.fn_att, fn.a0, fn.a1, d, a, b, f, fp);
+  edge_f_fp<FA, FR>(fn, d, a, b, f, fp);
   float gp = fp * inv_p;
   g = gp / d;
   if (!isfinite(g)) g = 1.0f;
 }
 
+template <int FA, int FR>
 __device__ __forceinline__ void edge_value(const FnDev& fn, float d, float a, float b, float& f) {
-  const bool rep = fn.push_pull && !(a >= 0.0f);
   float fp;
-  if (rep) eval_fn(fn.fn_rep, fn.r0, fn.r1, d, a, b, f, fp);
-  else eval_fn(fn.fn_att, fn.a0, fn.a1, d, a, b, f, fp);
+  edge_f_fp<FA, FR>(fn, d, a, b, f, fp);
 }
 
 // ------------------------------------------------------------------------------------------

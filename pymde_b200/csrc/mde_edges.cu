@@ -102,7 +102,7 @@ __device__ __forceinline__ void red_row(float* __restrict__ G, int r, const floa
 }
 
 // MODE 0: fused value + gradient; 1: value only; 2: external per-edge g (gradient only)
-template <int M, int MODE>
+template <int M, int MODE, int FA, int FR>
 __global__ void __launch_bounds__(kSmallThreads)
 distortion_small_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                         const float* __restrict__ par0, const float* __restrict__ par1,
@@ -121,15 +121,20 @@ distortion_small_kernel(const int32_t* __restrict__ src, const int32_t* __restri
     int s[kRounds], t[kRounds];
     float a[kRounds], b[kRounds];
     bool ok[kRounds];
+    // Out-of-range lanes re-read the last edge (index clamp) instead of selecting zeros: every lane
+    // then holds valid row indices and no address is formed from a predicated value.  (A zero-select
+    // on the 64-bit row offset compiled to `CS2R Rd, SRZ` + predicated IMAD.WIDE, which ptxas 12.9
+    // under-stalls on sm_100a -- see profiles/r01_ptxas_cs2r_hazard.md.)
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       int64_t k = base + r * 32 + lane;
       ok[r] = k < p;
-      s[r] = ok[r] ? __ldg(src + k) : 0;
-      t[r] = ok[r] ? __ldg(dst + k) : 0;
-      if (MODE == 2) a[r] = ok[r] ? __ldg(gext + __ldg(perm + k)) : 0.0f;
-      else a[r] = ok[r] ? __ldg(par0 + k) : 0.0f;
-      b[r] = (MODE != 2 && par1 != nullptr && ok[r]) ? __ldg(par1 + k) : 0.0f;
+      const int64_t kk = ok[r] ? k : (p - 1);
+      s[r] = __ldg(src + kk);
+      t[r] = __ldg(dst + kk);
+      if (MODE == 2) a[r] = __ldg(gext + __ldg(perm + kk));
+      else a[r] = __ldg(par0 + kk);
+      b[r] = (MODE != 2 && par1 != nullptr) ? __ldg(par1 + kk) : 0.0f;
     }
     Row<M> xi[kRounds], xj[kRounds];
 #pragma unroll
@@ -148,8 +153,8 @@ distortion_small_kernel(const int32_t* __restrict__ src, const int32_t* __restri
         g = a[r];
       } else {
         float d = sqrtf(d2), f;
-        if (MODE == 0) edge_coeff(fn, d, a[r], b[r], inv_p, f, g);
-        else { edge_value(fn, d, a[r], b[r], f); g = 0.0f; }
+        if (MODE == 0) edge_coeff<FA, FR>(fn, d, a[r], b[r], inv_p, f, g);
+        else { edge_value<FA, FR>(fn, d, a[r], b[r], f); g = 0.0f; }
         if (ok[r]) lsum += (double)f;
       }
       if (MODE != 1) {
@@ -215,6 +220,8 @@ distortion_wide_kernel(const int32_t* __restrict__ src, const int32_t* __restric
                        const int* __restrict__ flag) {
   if (flag != nullptr && *flag == 0) return;
   const int lg = threadIdx.x % G;
+  // shuffles stay inside the G-lane group: groups of one warp may run different trip counts
+  const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
   const int64_t group0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
   const int mv = m / VW;  // columns in units of VW floats
@@ -227,13 +234,15 @@ distortion_wide_kernel(const int32_t* __restrict__ src, const int32_t* __restric
     for (int c = 0; c < CPL; ++c)
 #pragma unroll
       for (int q = 0; q < VW; ++q) { xi[c].v[q] = 0.0f; acc[c].v[q] = 0.0f; }
-    // trip count is uniform across the warp (shuffles inside); work is predicated
+    // trip count is uniform across the group (shuffles inside); out-of-range iterations re-read the
+    // last edge / last column (clamped indices) and are masked out of every sum and store
     for (int it = 0; it < kWideSlice; ++it) {
-      int64_t k = k0 + it;
-      bool ok = k < p;
-      int s = ok ? __ldg(src + k) : cur;
-      int t = ok ? __ldg(dst + k) : 0;
-      if (s != cur) {
+      const int64_t k = k0 + it;
+      const bool ok = k < p;
+      const int64_t kk = ok ? k : (p - 1);
+      const int s = __ldg(src + kk);
+      const int t = __ldg(dst + kk);
+      if (ok && s != cur) {
         if (cur >= 0 && MODE != 1) {
 #pragma unroll
           for (int c = 0; c < CPL; ++c) {
@@ -244,36 +253,35 @@ distortion_wide_kernel(const int32_t* __restrict__ src, const int32_t* __restric
         cur = s;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
-          int col = lg + c * G;
+          const int col = lg + c * G;
+          const int colc = col < mv ? col : (mv - 1);
+          xi[c] = ldv<VW>(X + (int64_t)s * m + colc * VW);
 #pragma unroll
           for (int q = 0; q < VW; ++q) acc[c].v[q] = 0.0f;
-          if (col < mv) xi[c] = ldv<VW>(X + (int64_t)s * m + col * VW);
         }
       }
       Vec<VW> diff[CPL];
       float d2 = 0.0f;
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
-        int col = lg + c * G;
+        const int col = lg + c * G;
+        const int colc = col < mv ? col : (mv - 1);
+        const Vec<VW> xj = ldv<VW>(X + (int64_t)t * m + colc * VW);
+        const float keep = (col < mv) ? 1.0f : 0.0f;
 #pragma unroll
-        for (int q = 0; q < VW; ++q) diff[c].v[q] = 0.0f;
-        if (ok && col < mv) {
-          Vec<VW> xj = ldv<VW>(X + (int64_t)t * m + col * VW);
-#pragma unroll
-          for (int q = 0; q < VW; ++q) { diff[c].v[q] = xi[c].v[q] - xj.v[q]; d2 += diff[c].v[q] * diff[c].v[q]; }
-        }
+        for (int q = 0; q < VW; ++q) { diff[c].v[q] = (xi[c].v[q] - xj.v[q]) * keep; d2 += diff[c].v[q] * diff[c].v[q]; }
       }
 #pragma unroll
-      for (int off = G / 2; off > 0; off >>= 1) d2 += __shfl_xor_sync(kFull, d2, off);
+      for (int off = G / 2; off > 0; off >>= 1) d2 += __shfl_xor_sync(gmask, d2, off);
       float g, f = 0.0f;
       if (MODE == 2) {
-        g = ok ? __ldg(gext + __ldg(perm + k)) : 0.0f;
+        g = __ldg(gext + __ldg(perm + kk));
       } else {
-        float a = ok ? __ldg(par0 + k) : 1.0f;
-        float b = (ok && par1 != nullptr) ? __ldg(par1 + k) : 1.0f;
-        float d = sqrtf(d2);
-        if (MODE == 0) edge_coeff(fn, d, a, b, inv_p, f, g);
-        else { edge_value(fn, d, a, b, f); g = 0.0f; }
+        const float a = __ldg(par0 + kk);
+        const float b = (par1 != nullptr) ? __ldg(par1 + kk) : 1.0f;
+        const float d = sqrtf(d2);
+        if (MODE == 0) edge_coeff<-1, -1>(fn, d, a, b, inv_p, f, g);
+        else { edge_value<-1, -1>(fn, d, a, b, f); g = 0.0f; }
         if (ok && lg == 0) lsum += (double)f;
       }
       if (MODE != 1 && ok) {
@@ -334,7 +342,7 @@ __global__ void edge_outputs_kernel(const int32_t* __restrict__ src, const int32
   if (distances) distances[o] = d;
   if (distortions) {
     float f;
-    edge_value(fn, d, par0[k], par1 ? par1[k] : 0.0f, f);
+    edge_value<-1, -1>(fn, d, par0[k], par1 ? par1[k] : 0.0f, f);
     distortions[o] = f;
   }
 }
@@ -347,10 +355,8 @@ __global__ void function_eval_kernel(FnDev fn, const float* __restrict__ par0, i
   float a = par0[par0_len == 1 ? 0 : k];
   float b = par1 ? par1[k] : 0.0f;
   float d = dist[k];
-  const bool rep = fn.push_pull && !(a >= 0.0f);
   float f, fp;
-  if (rep) eval_fn(fn.fn_rep, fn.r0, fn.r1, d, a, b, f, fp);
-  else eval_fn(fn.fn_att, fn.a0, fn.a1, d, a, b, f, fp);
+  edge_f_fp<-1, -1>(fn, d, a, b, f, fp);
   if (f_out) f_out[k] = f;
   if (fp_out) fp_out[k] = fp;
 }
@@ -383,11 +389,25 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
   const float inv_p = 1.0f / (float)e->p_total;
   const int64_t p = e->p;
   int nb;
-#define SMALL(MM)                                                                                     \
-  nb = loss_blocks_small(p);                                                                          \
-  distortion_small_kernel<MM, MODE><<<nb, kSmallThreads, 0, st>>>(                                    \
+#define SMALLK(MM, FA, FR)                                                                            \
+  distortion_small_kernel<MM, MODE, FA, FR><<<nb, kSmallThreads, 0, st>>>(                            \
       e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
       e->loss_partials, e->fn, inv_p, flag)
+  // hot function combinations get compile-time ids (fused mode, m = 2 / 3); the rest use the table
+#define SMALL(MM)                                                                                     \
+  nb = loss_blocks_small(p);                                                                          \
+  if constexpr (MODE == 0 && (MM == 2 || MM == 3)) {                                                  \
+    const int fa = e->fn.fn_att, fr = e->fn.fn_rep, pp = e->fn.push_pull;                             \
+    if (pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOG) { SMALLK(MM, MDE_FN_P_LOG1P, MDE_FN_P_LOG); }            \
+    else if (pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOGRATIO) { SMALLK(MM, MDE_FN_P_LOG1P, MDE_FN_P_LOGRATIO); } \
+    else if (!pp && fa == MDE_FN_P_QUADRATIC) { SMALLK(MM, MDE_FN_P_QUADRATIC, MDE_FN_P_QUADRATIC); }             \
+    else if (!pp && fa == MDE_FN_P_LOG1P) { SMALLK(MM, MDE_FN_P_LOG1P, MDE_FN_P_LOG1P); }                         \
+    else if (!pp && fa == MDE_FN_L_ABSOLUTE) { SMALLK(MM, MDE_FN_L_ABSOLUTE, MDE_FN_L_ABSOLUTE); }                \
+    else if (!pp && fa == MDE_FN_L_QUADRATIC) { SMALLK(MM, MDE_FN_L_QUADRATIC, MDE_FN_L_QUADRATIC); }             \
+    else if (!pp && fa == MDE_FN_L_WEIGHTED_QUADRATIC) { SMALLK(MM, MDE_FN_L_WEIGHTED_QUADRATIC, MDE_FN_L_WEIGHTED_QUADRATIC); } \
+    else if (!pp && fa == MDE_FN_L_HUBER) { SMALLK(MM, MDE_FN_L_HUBER, MDE_FN_L_HUBER); }                         \
+    else { SMALLK(MM, -1, -1); }                                                                      \
+  } else { SMALLK(MM, -1, -1); }
 #define WIDE(GG, CC, VV)                                                                              \
   nb = loss_blocks_wide(p, GG);                                                                       \
   distortion_wide_kernel<GG, CC, VV, MODE><<<nb, kWideThreads, 0, st>>>(                              \
@@ -417,6 +437,7 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
     else return MDE_E_UNSUPPORTED;
   }
 #undef SMALL
+#undef SMALLK
 #undef WIDE
   MDE_LAUNCH_CHECK();
   if (nblocks_out) *nblocks_out = nb;
