@@ -199,6 +199,39 @@ __device__ __forceinline__ void edge_value(const FnDev& fn, float d, float a, fl
 }
 
 // ------------------------------------------------------------------------------------------
+// fast path for the recipe default PushAndPull(Log1p(1.5), Log(1.0)) (pymde/recipes.py:224-225):
+// MUFU approximations (rsqrt / sqrt / rcp / lg2 / ex2, <= 2 ulp each) instead of the IEEE
+// sequences.  The kernel is instruction-issue bound (profiles/r01_ncu_distortion.md), and only the
+// SUM of the per-edge losses has to agree with the reference to 1e-5: a 1e-7 absolute error per edge
+// is far inside that.  Inputs: squared distance d2.  Outputs: f_k and g_k = f'_k / (p d).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ void edge_coeff_fast_log1p_log(float d2, float w, float inv_p, float& f, float& g) {
+  const float kLn2 = 0.69314718056f, kLog2e = 1.44269504089f;
+  const float rs = fast_rsqrt(d2);          // 1/d  (inf at d2 = 0; masked by the caller)
+  const float d = (d2 > 0.0f) ? d2 * rs : 0.0f;  // 0 * inf would be NaN
+  if (w >= 0.0f) {                          // attractive: w log1p(d^1.5)
+    const float sd = fast_sqrt(d);
+    const float de = d * sd;
+    const float one_p = 1.0f + de;
+    f = w * kLn2 * fast_lg2(one_p);
+    g = w * (1.5f * inv_p) * sd * rs * fast_rcp(one_p);
+  } else {                                  // repulsive: w log(1 - exp(-d)),  f' = w / expm1(d)
+    const float em = fast_ex2(-d * kLog2e);                                      // e^-d
+    float one_m = 1.0f - em;                                                     // 1 - e^-d
+    const float series = d * (1.0f - d * (0.5f - d * (0.16666667f - d * 0.041666668f)));
+    one_m = (d < 0.0625f) ? series : one_m;                                      // no cancellation for small d
+    f = w * kLn2 * fast_lg2(one_m);
+    g = w * inv_p * rs * em * fast_rcp(one_m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

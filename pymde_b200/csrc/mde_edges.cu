@@ -19,6 +19,8 @@
 //   m >= 5 : a group of G lanes (8/16/32) walks a contiguous slice of edges; the lhs row and
 //            its gradient accumulator stay in registers across a run.
 #include <cub/cub.cuh>
+#include <cstdlib>
+#include <cstring>
 #include <new>
 
 #include "mde_common.cuh"
@@ -63,11 +65,13 @@ __global__ void unpack_kernel(const uint64_t* __restrict__ keys, const int32_t* 
                               int32_t* __restrict__ src, int32_t* __restrict__ dst,
                               float* __restrict__ p0, float* __restrict__ p1) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p) return;
-  uint64_t key = keys[k];
+  const int64_t p4 = (p + 3) & ~(int64_t)3;  // arrays are padded to a multiple of 4 edges
+  if (k >= p4) return;
+  const int64_t kk = k < p ? k : p - 1;     // pad entries repeat the last edge (masked in the kernels)
+  uint64_t key = keys[kk];
   src[k] = (int32_t)((key >> 32) & 0x7fffffffu);
   dst[k] = (int32_t)(key & 0xffffffffu);
-  int32_t o = vals[k];
+  int32_t o = vals[kk];
   p0[k] = par0[o];
   if (par1) p1[k] = par1[o];
 }
@@ -179,6 +183,96 @@ distortion_small_kernel(const int32_t* __restrict__ src, const int32_t* __restri
         if (head && ok[r]) red_row<M>(grad, s[r], v, 1.0f);
       }
     }
+  }
+  if (MODE != 2) {
+    __shared__ double sm[32];
+    double v1[1] = {lsum};
+    block_sum<1>(v1, sm);
+    if (threadIdx.x == 0) loss_partials[blockIdx.x] = v1[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// m <= 4, thread-contiguous variant: each thread owns 4 CONSECUTIVE sorted edges (three 16-byte
+// loads for src/dst/par0), sums the lhs contributions of equal-src runs in registers and issues one
+// red per run; no warp shuffles.  FAST selects the MUFU-based math for PushAndPull(Log1p(1.5), Log(1)).
+// ------------------------------------------------------------------------------------------
+static constexpr int kQuadThreads = 256;
+
+template <int M, int MODE, int FA, int FR, bool FAST>
+__global__ void __launch_bounds__(kQuadThreads)
+distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                       const float* __restrict__ par0, const float* __restrict__ par1,
+                       const int32_t* __restrict__ perm, const float* __restrict__ gext,
+                       int64_t p, const float* __restrict__ X, float* __restrict__ grad,
+                       double* __restrict__ loss_partials, FnDev fn, float inv_p,
+                       const int* __restrict__ flag) {
+  if (flag != nullptr && *flag == 0) return;
+  const int64_t nquads = (p + 3) >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float lsum_f = 0.0f;
+  double lsum = 0.0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+    const int4 s4 = __ldg(reinterpret_cast<const int4*>(src) + q);
+    const int4 t4 = __ldg(reinterpret_cast<const int4*>(dst) + q);
+    int s[4] = {s4.x, s4.y, s4.z, s4.w};
+    int t[4] = {t4.x, t4.y, t4.z, t4.w};
+    float a[4], b[4];
+    if (MODE == 2) {
+      const int4 o4 = __ldg(reinterpret_cast<const int4*>(perm) + q);  // pad entries repeat the last edge
+      a[0] = __ldg(gext + o4.x); a[1] = __ldg(gext + o4.y); a[2] = __ldg(gext + o4.z); a[3] = __ldg(gext + o4.w);
+    } else {
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(par0) + q);
+      a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+    }
+    if (MODE != 2 && par1 != nullptr) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(par1) + q);
+      b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+    } else { b[0] = b[1] = b[2] = b[3] = 0.0f; }
+    Row<M> xi[4], xj[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { xi[e] = load_row<M>(X, s[e]); xj[e] = load_row<M>(X, t[e]); }
+    float acc[M];
+#pragma unroll
+    for (int c = 0; c < M; ++c) acc[c] = 0.0f;
+    int cur = s[0];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool ok = (4 * q + e) < p;
+      float diff[M];
+      float d2 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < M; ++c) { diff[c] = xi[e].v[c] - xj[e].v[c]; d2 += diff[c] * diff[c]; }
+      float g, f = 0.0f;
+      if (MODE == 2) {
+        g = a[e];
+      } else if (FAST) {
+        edge_coeff_fast_log1p_log(d2, a[e], inv_p, f, g);
+      } else {
+        const float d = sqrtf(d2);
+        if (MODE == 0) edge_coeff<FA, FR>(fn, d, a[e], b[e], inv_p, f, g);
+        else { edge_value<FA, FR>(fn, d, a[e], b[e], f); g = 0.0f; }
+      }
+      if (MODE != 2 && ok) { if (FAST) lsum_f += f; else lsum += (double)f; }
+      if (MODE != 1) {
+        // d = 0: the reference replaces the non-finite g by 1 and the difference vector is 0
+        const bool live = ok && (FAST ? (d2 > 0.0f) : true);
+        float v[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) v[c] = live ? g * diff[c] : 0.0f;
+        if (live) red_row<M>(grad, t[e], v, -1.0f);
+        if (s[e] != cur) {  // run of equal src ended: flush its sum
+          red_row<M>(grad, cur, acc, 1.0f);
+          cur = s[e];
+#pragma unroll
+          for (int c = 0; c < M; ++c) acc[c] = 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < M; ++c) acc[c] += v[c];
+      }
+    }
+    if (MODE != 1) red_row<M>(grad, cur, acc, 1.0f);
+    if (FAST) { lsum += (double)lsum_f; lsum_f = 0.0f; }
   }
   if (MODE != 2) {
     __shared__ double sm[32];
@@ -374,6 +468,27 @@ int loss_blocks_small(int64_t p) {
   return (int)nb;
 }
 
+int loss_blocks_quad(int64_t p) {
+  int64_t per_block = (int64_t)kQuadThreads * 4;
+  int64_t nb = (p + per_block - 1) / per_block;
+  if (nb < 1) nb = 1;
+  if (nb > kNumSMs * 8) nb = kNumSMs * 8;
+  return (int)nb;
+}
+
+// A/B switch for measurements: MDE_B200_KERNEL=strided selects the lane-strided kernel with the warp
+// segmented reduction; MDE_B200_KERNEL=precise keeps the thread-contiguous kernel but IEEE math.
+int small_kernel_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDE_B200_KERNEL");
+    v = 0;
+    if (e && !strcmp(e, "strided")) v = 1;
+    if (e && !strcmp(e, "precise")) v = 2;
+  }
+  return v;
+}
+
 int loss_blocks_wide(int64_t p, int G) {
   int64_t groups_per_block = kWideThreads / G;
   int64_t per_block = groups_per_block * kWideSlice;
@@ -394,7 +509,31 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
       e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
       e->loss_partials, e->fn, inv_p, flag)
   // hot function combinations get compile-time ids (fused mode, m = 2 / 3); the rest use the table
+#define QUADK(MM, FA, FR, FAST)                                                                       \
+  distortion_quad_kernel<MM, MODE, FA, FR, FAST><<<nb, kQuadThreads, 0, st>>>(                        \
+      e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
+      e->loss_partials, e->fn, inv_p, flag)
 #define SMALL(MM)                                                                                     \
+  if (small_kernel_variant() != 1) {                                                                  \
+    nb = loss_blocks_quad(p);                                                                         \
+    const int fa = e->fn.fn_att, fr = e->fn.fn_rep, pp = e->fn.push_pull;                             \
+    const bool hot = pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOG && e->fn.a0 == 1.5f &&          \
+                     e->fn.r0 == 1.0f && small_kernel_variant() == 0;                                 \
+    if constexpr (MODE == 0 && (MM == 2 || MM == 3)) {                                                \
+      if (hot) { QUADK(MM, MDE_FN_P_LOG1P, MDE_FN_P_LOG, true); }                                     \
+      else if (pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOG) { QUADK(MM, MDE_FN_P_LOG1P, MDE_FN_P_LOG, false); } \
+      else if (pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOGRATIO) { QUADK(MM, MDE_FN_P_LOG1P, MDE_FN_P_LOGRATIO, false); } \
+      else if (!pp && fa == MDE_FN_P_QUADRATIC) { QUADK(MM, MDE_FN_P_QUADRATIC, MDE_FN_P_QUADRATIC, false); }     \
+      else if (!pp && fa == MDE_FN_L_ABSOLUTE) { QUADK(MM, MDE_FN_L_ABSOLUTE, MDE_FN_L_ABSOLUTE, false); }        \
+      else if (!pp && fa == MDE_FN_L_QUADRATIC) { QUADK(MM, MDE_FN_L_QUADRATIC, MDE_FN_L_QUADRATIC, false); }     \
+      else if (!pp && fa == MDE_FN_L_WEIGHTED_QUADRATIC) { QUADK(MM, MDE_FN_L_WEIGHTED_QUADRATIC, MDE_FN_L_WEIGHTED_QUADRATIC, false); } \
+      else if (!pp && fa == MDE_FN_L_HUBER) { QUADK(MM, MDE_FN_L_HUBER, MDE_FN_L_HUBER, false); }                 \
+      else { QUADK(MM, -1, -1, false); }                                                              \
+    } else { QUADK(MM, -1, -1, false); }                                                              \
+  } else {                                                                                            \
+    SMALL_STRIDED(MM);                                                                                \
+  }
+#define SMALL_STRIDED(MM)                                                                             \
   nb = loss_blocks_small(p);                                                                          \
   if constexpr (MODE == 0 && (MM == 2 || MM == 3)) {                                                  \
     const int fa = e->fn.fn_att, fr = e->fn.fn_rep, pp = e->fn.push_pull;                             \
@@ -437,6 +576,8 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
     else return MDE_E_UNSUPPORTED;
   }
 #undef SMALL
+#undef SMALL_STRIDED
+#undef QUADK
 #undef SMALLK
 #undef WIDE
   MDE_LAUNCH_CHECK();
@@ -497,10 +638,10 @@ int mde_edges_create(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t
   TRY(cudaMalloc(&keys_out, sizeof(uint64_t) * p));
   TRY(cudaMalloc(&vals_in, sizeof(int32_t) * p));
   TRY(cudaMalloc(&vals_out, sizeof(int32_t) * p));
-  TRY(cudaMalloc(&e->src, sizeof(int32_t) * p));
-  TRY(cudaMalloc(&e->dst, sizeof(int32_t) * p));
-  TRY(cudaMalloc(&e->par0, sizeof(float) * p));
-  if (par1) TRY(cudaMalloc(&e->par1, sizeof(float) * p));
+  TRY(cudaMalloc(&e->src, sizeof(int32_t) * (p + 4)));
+  TRY(cudaMalloc(&e->dst, sizeof(int32_t) * (p + 4)));
+  TRY(cudaMalloc(&e->par0, sizeof(float) * (p + 4)));
+  if (par1) TRY(cudaMalloc(&e->par1, sizeof(float) * (p + 4)));
   TRY(cudaMalloc(&e->loss_partials, sizeof(double) * kMaxLossBlocks));
   e->nbytes = p * (4 + 4 + 4 + 4 + (par1 ? 4 : 0)) + 8 * kMaxLossBlocks;
   {
@@ -512,7 +653,7 @@ int mde_edges_create(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t
     TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p, 0, 64, st));
     TRY(cudaMalloc(&tmp, tmp_bytes));
     TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p, 0, 64, st));
-    unpack_kernel<<<nb, tb, 0, st>>>(keys_out, vals_out, par0, par1, p, e->src, e->dst, e->par0, e->par1);
+    unpack_kernel<<<ceil_div_i64(p + 4, tb), tb, 0, st>>>(keys_out, vals_out, par0, par1, p, e->src, e->dst, e->par0, e->par1);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());
     TRY(cudaStreamSynchronize(st));

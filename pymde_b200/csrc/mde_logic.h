@@ -232,17 +232,17 @@ MDE_HD inline void ls_on_result(LsState& L, double f_new, float gtd_new, bool gr
 // L-BFGS history in Gram form
 // ---------------------------------------------------------------------------------------
 struct LbfgsState {
-  int n_iter;            // state["n_iter"] (0 after reset)
-  int count;             // pairs held
-  int order[kSlots];     // logical (oldest..newest) -> physical slot of S / Y
-  int cand;              // free physical slot receiving the candidate pair
-  int memory;            // history_size
-  double H_diag;
-  // coefficients of the new direction d = cg*g + sum_j cs[j]*S[order[j]] + cy[j]*Y[order[j]]
-  double cg, cs[kSlots], cy[kSlots];
   // Gram matrices in LOGICAL order: SY[i][j] = s_i . y_j, YY[i][j] = y_i . y_j
   double SY[kMaxMemory][kMaxMemory];
   double YY[kMaxMemory][kMaxMemory];
+  double H_diag;
+  // coefficients of the new direction d = cg*g + sum_j cs[j]*S[order[j]] + cy[j]*Y[order[j]]
+  double cg, cs[kSlots], cy[kSlots];
+  int n_iter;            // state["n_iter"] (0 after reset)
+  int count;             // pairs held
+  int cand;              // free physical slot receiving the candidate pair
+  int memory;            // history_size
+  int order[kSlots + 1]; // logical (oldest..newest) -> physical slot of S / Y (padded to an even count)
 };
 
 MDE_HD inline void lbfgs_reset(LbfgsState& B, int memory) {

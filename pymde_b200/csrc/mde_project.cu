@@ -148,10 +148,14 @@ colsum_wide_kernel(const float* __restrict__ X, int64_t n, int m, int mpad,
 __global__ void colmean_finalize_kernel(const double* __restrict__ partials, int nblocks, int64_t n, int m,
                                         double* __restrict__ mean, const int* active) {
   if (inactive(active)) return;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+  // one warp per column
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int k = gw; k < m; k += nw) {
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * m + k];
-    mean[k] = s / (double)n;
+    for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * m + k];
+    s = warp_sum(s);
+    if (lane == 0) mean[k] = s / (double)n;
   }
 }
 
@@ -216,12 +220,19 @@ proj_finalize_kernel(const double* __restrict__ partials, int nblocks, int64_t n
   __shared__ double sMu[kProjMaxM];
   const int K = m + m * m;
   const int Kuse = (MODE == 0) ? m : K;
-  // fixed-order reduction over blocks: one thread per output, serial over blocks
-  for (int k = threadIdx.x; k < Kuse; k += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * K + k];
-    if (k < m) sMu[k] = s / (double)n;
-    else sA[k - m] = s;
+  // fixed-order reduction over blocks: one WARP per output (lanes stride the blocks, then a
+  // shuffle tree) -- deterministic for a given launch shape, and ~nblocks/32 dependent loads deep
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = w; k < Kuse; k += nw) {
+      double s = 0.0;
+      for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * K + k];
+      s = warp_sum(s);
+      if (lane == 0) {
+        if (k < m) sMu[k] = s / (double)n;
+        else sA[k - m] = s;
+      }
+    }
   }
   __syncthreads();
   if (MODE != 2) {
@@ -395,7 +406,7 @@ int enqueue_project_centered(float* X, int64_t n, int m, const ProjWs& w, const 
     nb = blocks_for_rows(n, nrl * 8);
     colsum_wide_kernel<<<nb, kProjThreads, 0, st>>>(X, n, m, mpad, w.partials, active);
     MDE_LAUNCH_CHECK();
-    colmean_finalize_kernel<<<(m + 255) / 256, 256, 0, st>>>(w.partials, nb, n, m, w.mean, active);
+    colmean_finalize_kernel<<<(m + 7) / 8, 256, 0, st>>>(w.partials, nb, n, m, w.mean, active);
     MDE_LAUNCH_CHECK();
   }
   int64_t total = n * m;

@@ -63,6 +63,7 @@ struct SolverState {
   float gtd;       // g.d
   float dmax;      // max |d|
   double dd, xx;   // ||d||^2, ||X||^2 at iteration start
+  float mu_x[4], mu_d[4];  // column means of x_init and d (Centered, m in {1,2,4}: fused into the trial axpy)
   double t_last;   // state["t"]
   double t_eval;   // step of the most recent trial evaluation
   long long func_evals;
@@ -169,36 +170,143 @@ lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, cons
   }
 #pragma unroll
   for (int k = 0; k < kDotsPerSlice; ++k) dacc[k] += (double)acc[k];
-  __shared__ double sm[kDotsPerSlice * 32];
-  block_sum<kDotsPerSlice>(dacc, sm);
-  if (threadIdx.x == 0) {
-    double* o = part + ((int64_t)slice * gridDim.x + blockIdx.x) * kDotsPerSlice;
+  // block reduction through a transposed shared-memory tile: 44 x 256 fp32 partials, then each
+  // warp sums whole rows in fp64 (8 conflict-free loads per lane + one shuffle tree per row).
+  // ~10x fewer instructions than 44 independent shuffle trees per thread.
+  __shared__ float tile[kDotsPerSlice][kVecThreads];
 #pragma unroll
-    for (int k = 0; k < kDotsPerSlice; ++k) o[k] = dacc[k];
+  for (int k = 0; k < kDotsPerSlice; ++k) tile[k][threadIdx.x] = (float)dacc[k];
+  __syncthreads();
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* o = part + ((int64_t)slice * gridDim.x + blockIdx.x) * kDotsPerSlice;
+    for (int k = w; k < kDotsPerSlice; k += kVecThreads / 32) {
+      double sum = 0.0;
+#pragma unroll
+      for (int q = 0; q < kVecThreads / 32; ++q) sum += (double)tile[k][lane + 32 * q];
+      sum = warp_sum(sum);
+      if (lane == 0) o[k] = sum;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // S1: statistics of the iteration start + history update + two-loop in Gram form
 // ---------------------------------------------------------------------------------------
+// Block-cooperative version of mde_logic.h::lbfgs_direction (same decisions, same formulas): thread 0
+// takes the accept / evict decision, all threads move the Gram matrices, warp 0 runs the two-loop
+// recursion with lane j owning al_j and c_j (each step is one masked warp reduction instead of a
+// serial inner loop).  `dots` = [sj_yc | yj_yc | sc_yj | sj_g | yj_g], each kSlots long, in shared memory.
+__device__ void lbfgs_direction_block(LbfgsState& B, double* dots, double ys, double yy, double sc_g, double yc_g,
+                                      int* flags /* smem: [0]=first [1]=accepted [2]=evicted [3]=h before append */) {
+  double* sj_yc = dots; double* yj_yc = dots + kSlots; double* sc_yj = dots + 2 * kSlots;
+  double* sj_g = dots + 3 * kSlots; double* yj_g = dots + 4 * kSlots;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    B.n_iter += 1;
+    flags[0] = (B.n_iter == 1);
+    flags[1] = flags[2] = 0;
+    if (flags[0]) { B.count = 0; B.H_diag = 1.0; B.cg = -1.0; }
+    else if ((float)ys > 1e-10f) {
+      flags[1] = 1;
+      int h = B.count;
+      const int c = B.cand;
+      if (h == B.memory) {
+        flags[2] = 1;
+        const int freed = B.order[0];
+        for (int j = 1; j < h; ++j) B.order[j - 1] = B.order[j];
+        h -= 1;
+        B.order[h] = c; B.cand = freed;
+      } else {
+        B.order[h] = c;
+        unsigned long long used = 0ull;
+        for (int j = 0; j <= h; ++j) used |= 1ull << B.order[j];
+        int f = 0;
+        while (f < kSlots - 1 && ((used >> f) & 1ull)) ++f;
+        B.cand = f;
+      }
+      flags[3] = h;
+      B.count = h + 1;
+      B.H_diag = (double)((float)ys / (float)yy);
+    }
+  }
+  __syncthreads();
+  if (flags[0]) return;
+  if (flags[2]) {  // evict the oldest pair: shift matrices and dot arrays up-left by one
+    const int h_old = flags[3] + 1;
+    double a[4], b[4];
+    int n = 0;
+    for (int k = tid; k < (h_old - 1) * (h_old - 1); k += blockDim.x) {
+      int i = k / (h_old - 1) + 1, j = k % (h_old - 1) + 1;
+      a[n] = B.SY[i][j]; b[n] = B.YY[i][j]; ++n;
+    }
+    double v[5] = {0, 0, 0, 0, 0};
+    if (tid >= 1 && tid < h_old) { v[0] = sj_yc[tid]; v[1] = yj_yc[tid]; v[2] = sc_yj[tid]; v[3] = sj_g[tid]; v[4] = yj_g[tid]; }
+    __syncthreads();
+    n = 0;
+    for (int k = tid; k < (h_old - 1) * (h_old - 1); k += blockDim.x) {
+      int i = k / (h_old - 1), j = k % (h_old - 1);
+      B.SY[i][j] = a[n]; B.YY[i][j] = b[n]; ++n;
+    }
+    if (tid >= 1 && tid < h_old) { sj_yc[tid - 1] = v[0]; yj_yc[tid - 1] = v[1]; sc_yj[tid - 1] = v[2]; sj_g[tid - 1] = v[3]; yj_g[tid - 1] = v[4]; }
+    __syncthreads();
+  }
+  if (flags[1]) {  // append the candidate as the newest pair
+    const int h = flags[3];
+    if (tid < h) {
+      B.SY[tid][h] = sj_yc[tid]; B.SY[h][tid] = sc_yj[tid];
+      B.YY[tid][h] = yj_yc[tid]; B.YY[h][tid] = yj_yc[tid];
+    }
+    if (tid == 0) { B.SY[h][h] = ys; B.YY[h][h] = yy; sj_g[h] = sc_g; yj_g[h] = yc_g; }
+    __syncthreads();
+  }
+  if (tid < 32) {  // two-loop recursion (lbfgs.py:488-507) on the Gram matrices
+    const int lane = tid, h = B.count;
+    const double H = B.H_diag;
+    double al = 0.0, cc = 0.0;
+    for (int i = h - 1; i >= 0; --i) {
+      double term = (lane > i && lane < h) ? al * B.SY[i][lane] : 0.0;
+      double sq = -sj_g[i] - warp_sum(term);
+      double ali = sq / B.SY[i][i];
+      if (lane == i) al = ali;
+    }
+    for (int i = 0; i < h; ++i) {
+      double t1 = (lane < h) ? al * B.YY[i][lane] : 0.0;
+      double yq = -yj_g[i] - warp_sum(t1);
+      double t2 = (lane < i) ? cc * B.SY[lane][i] : 0.0;
+      double yr = H * yq + warp_sum(t2);
+      double be = yr / B.SY[i][i];
+      double ali = __shfl_sync(kFull, al, i);
+      if (lane == i) cc = ali - be;
+    }
+    if (lane < h) { B.cs[lane] = cc; B.cy[lane] = -H * al; }
+    if (lane == 0) B.cg = -H;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 direction_scalar_kernel(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks) {
   if (off(&S->active)) return;
   __shared__ double sums[kMaxSlices * kDotsPerSlice];
-  __shared__ double sSY[kMaxMemory][kMaxMemory];
-  __shared__ double sYY[kMaxMemory][kMaxMemory];
-  const int count = S->lb.count;
-  const int n_iter = S->lb.n_iter;
+  __shared__ double dots[5 * kSlots];
+  __shared__ int flags[4];
+  __shared__ LbfgsState sB;  // the whole history state (Gram matrices included) staged in shared memory
+  static_assert(sizeof(LbfgsState) % sizeof(double) == 0, "LbfgsState must be a whole number of doubles");
+  static_assert(kMaxMemory <= 32, "the two-loop recursion maps one pair per lane");
+  {
+    const double* src = reinterpret_cast<const double*>(&S->lb);
+    double* dst = reinterpret_cast<double*>(&sB);
+    for (int k = threadIdx.x; k < (int)(sizeof(LbfgsState) / sizeof(double)); k += blockDim.x) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int count = sB.count;
+  const int n_iter = sB.n_iter;
   int slices = (count + kPairsPerSlice - 1) / kPairsPerSlice;
   if (slices < 1) slices = 1;
   if (n_iter > 0) {
     for (int s = 0; s < slices; ++s)
       reduce_partials<false>(part + (int64_t)s * nblocks * kDotsPerSlice, nblocks, kDotsPerSlice,
                              sums + s * kDotsPerSlice);
-    for (int k = threadIdx.x; k < kMaxMemory * kMaxMemory; k += blockDim.x) {
-      (&sSY[0][0])[k] = (&S->lb.SY[0][0])[k];
-      (&sYY[0][0])[k] = (&S->lb.YY[0][0])[k];
-    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -207,21 +315,21 @@ direction_scalar_kernel(SolverState* __restrict__ S, const double* __restrict__ 
     const double resid = (double)sqrtf((float)S->gg);
     if (it < S->max_stats) { S->avg[it] = S->loss; S->resid[it] = resid; }
     S->stop_after = (resid <= S->eps) ? 1 : 0;
-    double sj_yc[kMaxMemory + 1], yj_yc[kMaxMemory + 1], sc_yj[kMaxMemory + 1], sj_g[kMaxMemory + 1], yj_g[kMaxMemory + 1];
-    for (int j = 0; j < count; ++j) {
-      const double* b = sums + (j / kPairsPerSlice) * kDotsPerSlice + 4 + 5 * (j % kPairsPerSlice);
-      sj_yc[j] = b[0]; yj_yc[j] = b[1]; sc_yj[j] = b[2]; sj_g[j] = b[3]; yj_g[j] = b[4];
-    }
-    LbfgsState& B = S->lb;
-    if (n_iter > 0) lbfgs_direction(B, sSY, sYY, sums[0], sums[1], sums[2], sums[3], sj_yc, yj_yc, sc_yj, sj_g, yj_g);
-    else lbfgs_direction(B, sSY, sYY, 0, 0, 0, 0, sj_yc, yj_yc, sc_yj, sj_g, yj_g);
+  }
+  if (threadIdx.x < count) {
+    const int j = threadIdx.x;
+    const double* b = sums + (j / kPairsPerSlice) * kDotsPerSlice + 4 + 5 * (j % kPairsPerSlice);
+    dots[j] = b[0]; dots[kSlots + j] = b[1]; dots[2 * kSlots + j] = b[2]; dots[3 * kSlots + j] = b[3];
+    dots[4 * kSlots + j] = b[4];
   }
   __syncthreads();
-  if (n_iter > 0) {
-    for (int k = threadIdx.x; k < kMaxMemory * kMaxMemory; k += blockDim.x) {
-      (&S->lb.SY[0][0])[k] = (&sSY[0][0])[k];
-      (&S->lb.YY[0][0])[k] = (&sYY[0][0])[k];
-    }
+  if (n_iter > 0) lbfgs_direction_block(sB, dots, sums[0], sums[1], sums[2], sums[3], flags);
+  else lbfgs_direction_block(sB, dots, 0.0, 0.0, 0.0, 0.0, flags);
+  __syncthreads();
+  {
+    double* dst = reinterpret_cast<double*>(&S->lb);
+    const double* src = reinterpret_cast<const double*>(&sB);
+    for (int k = threadIdx.x; k < (int)(sizeof(LbfgsState) / sizeof(double)); k += blockDim.x) dst[k] = src[k];
   }
 }
 
@@ -232,7 +340,7 @@ __global__ void __launch_bounds__(kVecThreads)
 direction_apply_kernel(const SolverState* __restrict__ S, const float* __restrict__ g, float* __restrict__ gprev,
                        float* __restrict__ d, const float* __restrict__ X, float* __restrict__ xinit,
                        const float* __restrict__ Sb, const float* __restrict__ Yb, int64_t npad,
-                       double* __restrict__ part) {
+                       double* __restrict__ part, int mcols) {
   if (off(&S->active)) return;
   __shared__ float cs[kMaxMemory], cy[kMaxMemory];
   __shared__ const float* ps[kMaxMemory];
@@ -247,8 +355,11 @@ direction_apply_kernel(const SolverState* __restrict__ S, const float* __restric
     py[threadIdx.x] = Yb + (int64_t)q * npad;
   }
   __syncthreads();
-  double acc[3] = {0.0, 0.0, 0.0};
-  float fa[3] = {0.0f, 0.0f, 0.0f};
+  constexpr int KA = 11;  // g.d, d.d, X.X, column sums of X (4) and of d (4)
+  double acc[KA];
+  float fa[KA];
+#pragma unroll
+  for (int k = 0; k < KA; ++k) { acc[k] = 0.0; fa[k] = 0.0f; }
   float mx = 0.0f;
   const int64_t n4 = npad >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -270,60 +381,109 @@ direction_apply_kernel(const SolverState* __restrict__ S, const float* __restric
     fa[1] += r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
     fa[2] += Xv.x * Xv.x + Xv.y * Xv.y + Xv.z * Xv.z + Xv.w * Xv.w;
     mx = fmaxf(mx, fmaxf(fmaxf(fabsf(r[0]), fabsf(r[1])), fmaxf(fabsf(r[2]), fabsf(r[3]))));
+    // column sums (rows are m floats; 4 % m == 0 so element q of a float4 belongs to column q % m)
+    if (mcols == 1) {
+      fa[3] += Xv.x + Xv.y + Xv.z + Xv.w; fa[7] += r[0] + r[1] + r[2] + r[3];
+    } else if (mcols == 2) {
+      fa[3] += Xv.x + Xv.z; fa[4] += Xv.y + Xv.w; fa[7] += r[0] + r[2]; fa[8] += r[1] + r[3];
+    } else if (mcols == 4) {
+      fa[3] += Xv.x; fa[4] += Xv.y; fa[5] += Xv.z; fa[6] += Xv.w;
+      fa[7] += r[0]; fa[8] += r[1]; fa[9] += r[2]; fa[10] += r[3];
+    }
     if (++cnt == 16) {
-      for (int k = 0; k < 3; ++k) { acc[k] += (double)fa[k]; fa[k] = 0.0f; }
+#pragma unroll
+      for (int k = 0; k < KA; ++k) { acc[k] += (double)fa[k]; fa[k] = 0.0f; }
       cnt = 0;
     }
   }
-  for (int k = 0; k < 3; ++k) acc[k] += (double)fa[k];
-  __shared__ double sm[3 * 32];
+#pragma unroll
+  for (int k = 0; k < KA; ++k) acc[k] += (double)fa[k];
+  __shared__ double sm[KA * 32];
   __shared__ float smx[32];
-  block_sum<3>(acc, sm);
+  block_sum<KA>(acc, sm);
   mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
   __syncthreads();
   if (threadIdx.x == 0) {
     float m2 = 0.0f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m2 = fmaxf(m2, smx[w]);
-    double* o = part + (int64_t)blockIdx.x * 4;
-    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = (double)m2;
+    double* o = part + (int64_t)blockIdx.x * (KA + 1);
+#pragma unroll
+    for (int k = 0; k < KA; ++k) o[k] = acc[k];
+    o[KA] = (double)m2;
   }
 }
 
 // S2: finalize g.d, |d|, |X|; initial step; arm the line search (lbfgs.py:521-549)
 __global__ void __launch_bounds__(256)
-ls_init_kernel(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks) {
+ls_init_kernel(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks, int64_t n_rows,
+               cudaGraphConditionalHandle h_while) {
   if (off(&S->active)) return;
-  __shared__ double out[4];
-  reduce_partials<true>(part, nblocks, 4, out);
+  __shared__ double out[12];
+  reduce_partials<true>(part, nblocks, 12, out);
   if (threadIdx.x == 0) {
-    S->gtd = (float)out[0]; S->dd = out[1]; S->xx = out[2]; S->dmax = (float)out[3];
+    S->gtd = (float)out[0]; S->dd = out[1]; S->xx = out[2]; S->dmax = (float)out[11];
+    const double inv_n = 1.0 / (double)n_rows;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { S->mu_x[c] = (float)(out[3 + c] * inv_n); S->mu_d[c] = (float)(out[7 + c] * inv_n); }
     double t0 = 1.0;
     if (S->lb.n_iter == 1) {  // t = min(1, 1/||g||_1) * lr
       float inv = 1.0f / (float)S->g1;
       t0 = (inv < 1.0f) ? (double)inv : 1.0;
     }
-    ls_begin(S->ls, t0, S->loss, S->gtd, S->dmax);
+    LsState L;
+    ls_begin(L, t0, S->loss, (float)out[0], (float)out[11]);
+    S->ls = L;
     S->ls_active = 1;
+    if (h_while) cudaGraphSetConditional(h_while, 1u);  // enter the device-side trial loop
   }
+}
+
+// graph mode: gate of the IF node around the fresh evaluation
+__global__ void fresh_gate_kernel(const SolverState* __restrict__ S, cudaGraphConditionalHandle h_if) {
+  if (threadIdx.x == 0) cudaGraphSetConditional(h_if, (S->active && S->need_fresh) ? 1u : 0u);
 }
 
 // ---------------------------------------------------------------------------------------
 // trial point: X = x_init + t*d  (LBFGS._add_grad, lbfgs.py:350-357); FINAL uses t_accept
 // ---------------------------------------------------------------------------------------
+// center_m = 0: plain axpy.  center_m in {1,2,4}: the Centered projection (constraints.py:106-111) is
+// folded in analytically, mean(x_init + t d) = mean(x_init) + t mean(d) with both means taken in the
+// direction pass, so a trial point costs one pass and no reduction.  `gz` (trial only): gradient buffer
+// zeroed in the same pass for the scatter kernel that follows.
 template <bool FINAL>
 __global__ void __launch_bounds__(kVecThreads)
 trial_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, const float* __restrict__ d,
-                  float* __restrict__ X, int64_t npad) {
+                  float* __restrict__ X, int64_t npad, int64_t nvalid, int center_m, float* __restrict__ gz) {
   if (off(&S->active)) return;
   if (!FINAL && off(&S->ls_active)) return;
   const float t = FINAL ? (float)S->ls.t_accept : (float)S->ls.t;
+  float mu[4] = {0.f, 0.f, 0.f, 0.f};
+  if (center_m == 1) { float v = S->mu_x[0] + t * S->mu_d[0]; mu[0] = mu[1] = mu[2] = mu[3] = v; }
+  else if (center_m == 2) {
+    float v0 = S->mu_x[0] + t * S->mu_d[0], v1 = S->mu_x[1] + t * S->mu_d[1];
+    mu[0] = mu[2] = v0; mu[1] = mu[3] = v1;
+  } else if (center_m == 4) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mu[c] = S->mu_x[c] + t * S->mu_d[c];
+  }
   const int64_t n4 = npad >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 A = reinterpret_cast<const float4*>(xinit)[i];
-    float4 D = reinterpret_cast<const float4*>(d)[i];
-    reinterpret_cast<float4*>(X)[i] = make_float4(fmaf(t, D.x, A.x), fmaf(t, D.y, A.y), fmaf(t, D.z, A.z), fmaf(t, D.w, A.w));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + 1; i += stride) {
+    if (i < n4) {
+      float4 A = reinterpret_cast<const float4*>(xinit)[i];
+      float4 D = reinterpret_cast<const float4*>(d)[i];
+      float4 R = make_float4(fmaf(t, D.x, A.x) - mu[0], fmaf(t, D.y, A.y) - mu[1], fmaf(t, D.z, A.z) - mu[2],
+                             fmaf(t, D.w, A.w) - mu[3]);
+      if (center_m != 0 && 4 * i + 3 >= nvalid) {  // keep the zero padding behind the last row
+        if (4 * i + 0 >= nvalid) R.x = 0.f;
+        if (4 * i + 1 >= nvalid) R.y = 0.f;
+        if (4 * i + 2 >= nvalid) R.z = 0.f;
+        if (4 * i + 3 >= nvalid) R.w = 0.f;
+      }
+      reinterpret_cast<float4*>(X)[i] = R;
+    }
+    if (!FINAL && gz != nullptr) reinterpret_cast<float4*>(gz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -414,14 +574,19 @@ fresh_finish_kernel(SolverState* __restrict__ S, const double* __restrict__ lpar
   if (threadIdx.x == 0) {
     S->loss = loss; S->gg = out[1]; S->g1 = out[2];
     S->func_evals += 1;
+    S->pad0 = (int)S->func_evals;
   }
 }
 
 // S(trial): feed (f_new, g.d) to the Wolfe state machine; decide the next step or finish
 __global__ void __launch_bounds__(256)
 ls_update_kernel(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
-                 const float* __restrict__ tail, const double* __restrict__ dpart, int nd, double p_total) {
-  if (off(&S->active) || off(&S->ls_active)) return;
+                 const float* __restrict__ tail, const double* __restrict__ dpart, int nd, double p_total,
+                 cudaGraphConditionalHandle h_while) {
+  if (off(&S->active) || off(&S->ls_active)) {
+    if (h_while && threadIdx.x == 0) cudaGraphSetConditional(h_while, 0u);
+    return;
+  }
   __shared__ double out[3];
   __shared__ double l1[1];
   double loss = eval_loss(S, lpart, nl, tail, l1, p_total);
@@ -429,15 +594,19 @@ ls_update_kernel(SolverState* __restrict__ S, const double* __restrict__ lpart, 
   if (threadIdx.x == 0) {
     S->gg = out[1]; S->g1 = out[2];
     S->func_evals += 1;
-    S->t_eval = S->ls.t;
+    S->pad0 = (int)S->func_evals;
+    LsState L = S->ls;  // work on a register copy: the state machine touches ~30 fields
+    S->t_eval = L.t;
     const bool finite = isfinite(out[1]);
-    ls_on_result(S->ls, loss, (float)out[0], finite);
-    if (S->ls.phase == LS_DONE) {
+    ls_on_result(L, loss, (float)out[0], finite);
+    S->ls = L;
+    if (L.phase == LS_DONE) {
       S->ls_active = 0;
-      if (S->ls.error) { S->error = MDE_E_NAN; S->active = 0; }
-      S->t_last = S->ls.t_accept;
-      S->loss = (double)(float)S->ls.f_accept;  // _cached_loss is an fp32 tensor (lbfgs.py:550)
+      if (L.error) { S->error = MDE_E_NAN; S->active = 0; }
+      S->t_last = L.t_accept;
+      S->loss = (double)(float)L.f_accept;  // _cached_loss is an fp32 tensor (lbfgs.py:550)
     }
+    if (h_while) cudaGraphSetConditional(h_while, (S->ls_active && S->active) ? 1u : 0u);
   }
 }
 
@@ -491,14 +660,22 @@ struct mde_solver {
   double *stats = nullptr;           // 4 * max_iter doubles
   void* projws = nullptr;
   ProjWs pw{};
+  int center_m = 0;                  // {1,2,4}: Centered projection fused into the trial axpy
   int nl = 0;                        // loss-partial blocks of the distortion launch
   int nvb = 0;                       // vector-pass blocks
   int host_need_fresh = 1;
   int host_active = 0;
+  int host_evals = 0;                // func_evals already accounted in the launch counter (mode 1)
   mde_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
   int64_t* anchors = nullptr;
   float* anchor_values = nullptr;
+  // mode 1: one CUDA graph per iteration with an IF node (fresh evaluation) and a WHILE node (trials)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr, cap_stream2 = nullptr;
+  cudaGraphConditionalHandle h_if = 0, h_while = 0;
+  int graph_kernels_fixed = 0, graph_kernels_trial = 0, graph_kernels_fresh = 0;
 };
 
 namespace {
@@ -513,7 +690,9 @@ int read_status(mde_solver* s, cudaStream_t st) {
 int enqueue_project(mde_solver* s, cudaStream_t st) {
   const int* act = &s->S->active;
   switch (s->opts.constraint) {
-    case MDE_CONSTRAINT_CENTERED: return enqueue_project_centered(s->X, s->n, s->m, s->pw, act, st);
+    case MDE_CONSTRAINT_CENTERED:
+      if (s->center_m) return 0;  // already applied by trial_axpy_kernel
+      return enqueue_project_centered(s->X, s->n, s->m, s->pw, act, st);
     case MDE_CONSTRAINT_STANDARDIZED: return enqueue_project_standardized(s->X, s->n, s->m, s->pw, act, st);
     case MDE_CONSTRAINT_ANCHORED: {
       int64_t tot = s->opts.n_anchors * s->m;
@@ -529,10 +708,12 @@ int enqueue_project(mde_solver* s, cudaStream_t st) {
 }
 
 // closure: value_and_grad at s->X (optim.py:100-105); `flag` gates the kernels
-int enqueue_eval(mde_solver* s, const int* flag, cudaStream_t st) {
-  const int64_t n4 = (s->npad + 4) >> 2;  // gradient + (hi, lo) tail
-  zero_kernel<<<vec_blocks(n4), kVecThreads, 0, st>>>(flag, s->g, n4);
-  MDE_LAUNCH_CHECK();
+int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, cudaStream_t st) {
+  if (zero_g) {
+    const int64_t n4 = (s->npad + 4) >> 2;  // gradient + (hi, lo) tail
+    zero_kernel<<<vec_blocks(n4), kVecThreads, 0, st>>>(flag, s->g, n4);
+    MDE_LAUNCH_CHECK();
+  }
   int rc = distortion_fused_flag(s->edges, s->X, s->m, s->g, &s->nl, flag, st);
   if (rc) return rc;
   if (s->opts.world_size > 1) {
@@ -560,7 +741,7 @@ int enqueue_eval(mde_solver* s, const int* flag, cudaStream_t st) {
 }
 
 int enqueue_fresh(mde_solver* s, cudaStream_t st) {
-  int rc = enqueue_eval(s, &s->S->need_fresh, st);
+  int rc = enqueue_eval(s, &s->S->need_fresh, true, st);
   if (rc) return rc;
   fresh_finish_kernel<<<1, 256, 0, st>>>(s->S, loss_partials_ptr(s->edges), s->nl, s->g + s->npad, s->dpart,
                                          s->nvb, (double)edges_p_total(s->edges));
@@ -576,34 +757,105 @@ int enqueue_direction(mde_solver* s, cudaStream_t st) {
   direction_scalar_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb);
   MDE_LAUNCH_CHECK();
   direction_apply_kernel<<<s->nvb, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->X, s->xinit, s->Sb,
-                                                         s->Yb, s->npad, s->dpart);
+                                                         s->Yb, s->npad, s->dpart, s->center_m);
   MDE_LAUNCH_CHECK();
-  ls_init_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb);
+  ls_init_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb, s->n, s->h_while);
   MDE_LAUNCH_CHECK();
   return 0;
 }
 
 int enqueue_trial(mde_solver* s, cudaStream_t st) {
-  trial_axpy_kernel<false><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad);
+  trial_axpy_kernel<false><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, s->g);
   MDE_LAUNCH_CHECK();
   int rc = enqueue_project(s, st);
   if (rc) return rc;
-  rc = enqueue_eval(s, &s->S->ls_active, st);
+  rc = enqueue_eval(s, &s->S->ls_active, false, st);
   if (rc) return rc;
   ls_update_kernel<<<1, 256, 0, st>>>(s->S, loss_partials_ptr(s->edges), s->nl, s->g + s->npad, s->dpart, s->nvb,
-                                      (double)edges_p_total(s->edges));
+                                      (double)edges_p_total(s->edges), s->h_while);
   MDE_LAUNCH_CHECK();
   return 0;
 }
 
 int enqueue_finish(mde_solver* s, cudaStream_t st) {
-  trial_axpy_kernel<true><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad);
+  trial_axpy_kernel<true><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, nullptr);
   MDE_LAUNCH_CHECK();
   int rc = enqueue_project(s, st);
   if (rc) return rc;
   iter_end_kernel<<<1, 32, 0, st>>>(s->S);
   MDE_LAUNCH_CHECK();
   return 0;
+}
+
+// One iteration as a CUDA graph:
+//   fresh_gate -> IF(need_fresh){ evaluate at X } -> direction (P1,S1,P2,S2) -> WHILE(ls_active){ trial }
+//   -> accepted step + projection + iter_end.
+// The conditional handles are written on the device (cudaGraphSetConditional), so the host never reads
+// a scalar during an iteration.
+int build_iteration_graph(mde_solver* s) {
+#define GTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
+  GTRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+  GTRY(cudaStreamCreateWithFlags(&s->cap_stream2, cudaStreamNonBlocking));
+  cudaStream_t st = s->cap_stream, st2 = s->cap_stream2;
+  cudaStreamCaptureStatus cs;
+  cudaGraph_t cg = nullptr;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t nd = 0;
+  int rc;
+  const unsigned long long l0 = g_launch_count;
+  GTRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  GTRY(cudaStreamGetCaptureInfo_v2(st, &cs, nullptr, &cg, &deps, &nd));
+  GTRY(cudaGraphConditionalHandleCreate(&s->h_if, cg, 0, cudaGraphCondAssignDefault));
+  GTRY(cudaGraphConditionalHandleCreate(&s->h_while, cg, 0, cudaGraphCondAssignDefault));
+  fresh_gate_kernel<<<1, 32, 0, st>>>(s->S, s->h_if);
+  ++g_launch_count;
+  GTRY(cudaPeekAtLastError());
+  {  // IF node: closure() at the current iterate when lbfgs n_iter == 0
+    GTRY(cudaStreamGetCaptureInfo_v2(st, &cs, nullptr, &cg, &deps, &nd));
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = s->h_if;
+    np.conditional.type = cudaGraphCondTypeIf;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    GTRY(cudaGraphAddNode(&node, cg, deps, nd, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    GTRY(cudaStreamBeginCaptureToGraph(st2, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    const unsigned long long a = g_launch_count;
+    rc = enqueue_fresh(s, st2);
+    s->graph_kernels_fresh = (int)(g_launch_count - a);
+    cudaError_t e = cudaStreamEndCapture(st2, nullptr);
+    if (rc) return rc;
+    GTRY(e);
+    GTRY(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+  }
+  if ((rc = enqueue_direction(s, st))) return rc;
+  {  // WHILE node: line-search trials
+    GTRY(cudaStreamGetCaptureInfo_v2(st, &cs, nullptr, &cg, &deps, &nd));
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = s->h_while;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    GTRY(cudaGraphAddNode(&node, cg, deps, nd, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    GTRY(cudaStreamBeginCaptureToGraph(st2, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    const unsigned long long a = g_launch_count;
+    rc = enqueue_trial(s, st2);
+    s->graph_kernels_trial = (int)(g_launch_count - a);
+    cudaError_t e = cudaStreamEndCapture(st2, nullptr);
+    if (rc) return rc;
+    GTRY(e);
+    GTRY(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+  }
+  if ((rc = enqueue_finish(s, st))) return rc;
+  GTRY(cudaStreamEndCapture(st, &s->graph));
+  GTRY(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+  s->graph_kernels_fixed = (int)(g_launch_count - l0) - s->graph_kernels_trial - s->graph_kernels_fresh;
+  g_launch_count = l0;  // capture enqueued nothing; launches are counted per graph launch
+  return 0;
+#undef GTRY
 }
 
 }  // namespace
@@ -617,7 +869,8 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   if (opts->constraint == MDE_CONSTRAINT_STANDARDIZED && m > kProjMaxM) return MDE_E_UNSUPPORTED;
   if (opts->constraint < 0 || opts->constraint > MDE_CONSTRAINT_ANCHORED) return MDE_E_INVALID;
   if (opts->max_iter < 1) return MDE_E_INVALID;
-  if (opts->mode != 0) return MDE_E_UNSUPPORTED;
+  if (opts->mode != 0 && opts->mode != 1) return MDE_E_INVALID;
+  if (opts->mode == 1 && opts->world_size > 1) return MDE_E_UNSUPPORTED;  // NCCL hook is host-stepped
   if (n != edges_n(e)) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   mde_solver* s = new (std::nothrow) mde_solver();
@@ -651,6 +904,13 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
                         cudaMemcpyDeviceToDevice, st));
   }
   s->nvb = vec_blocks(s->npad >> 2);
+  if (opts->constraint == MDE_CONSTRAINT_CENTERED && (m == 1 || m == 2 || m == 4)) s->center_m = m;
+  if (opts->mode == 1) {
+    s->nl = 0;
+    TRY(cudaStreamSynchronize(st));
+    rc = build_iteration_graph(s);
+    if (rc) goto fail;
+  }
   *out = s;
   return 0;
 fail:
@@ -665,6 +925,10 @@ int mde_solver_destroy(mde_solver_t* s) {
   cudaFree(s->X); cudaFree(s->xinit); cudaFree(s->d); cudaFree(s->g); cudaFree(s->gprev);
   cudaFree(s->Sb); cudaFree(s->Yb); cudaFree(s->dpart); cudaFree(s->stats); cudaFree(s->projws);
   cudaFree(s->anchors); cudaFree(s->anchor_values);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  if (s->graph) cudaGraphDestroy(s->graph);
+  if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+  if (s->cap_stream2) cudaStreamDestroy(s->cap_stream2);
   delete s;
   return 0;
 }
@@ -685,6 +949,7 @@ int mde_solver_begin(mde_solver_t* s, const float* X0, double eps, void* stream)
   MDE_LAUNCH_CHECK();
   s->host_need_fresh = 1;
   s->host_active = 1;
+  s->host_evals = 0;
   return 0;
 }
 
@@ -692,6 +957,27 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
   if (!s) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = 0;
+  if (s->opts.mode == 1) {
+    // device-driven: one graph launch per iteration, status read back once per batch.  Launches
+    // after convergence are no-ops (every kernel checks the device-side `active` flag).
+    int left = iters;
+    while (left > 0 && s->host_active) {
+      const int batch = left < 16 ? left : 16;
+      for (int b = 0; b < batch; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->graph_exec, st));
+      left -= batch;
+      if ((rc = read_status(s, st))) return rc;
+      s->host_active = s->status_host[0];
+      // kernels executed by the graphs: fixed part per launch + one trial body per evaluation
+      g_launch_count += (unsigned long long)batch * s->graph_kernels_fixed +
+                        (unsigned long long)(s->status_host[7] - s->host_evals) * s->graph_kernels_trial;
+      s->host_evals = s->status_host[7];
+      if (s->status_host[3]) { if (iters_done) *iters_done = s->status_host[2]; return s->status_host[3]; }
+    }
+    if ((rc = read_status(s, st))) return rc;
+    if (iters_done) *iters_done = s->status_host[2];
+    if (converged) *converged = s->status_host[1];
+    return 0;
+  }
   for (int it = 0; it < iters && s->host_active; ++it) {
     if (s->host_need_fresh) { if ((rc = enqueue_fresh(s, st))) return rc; }
     if ((rc = enqueue_direction(s, st))) return rc;

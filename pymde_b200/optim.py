@@ -6,6 +6,7 @@ distortion function and constraint the CUDA path supports, the whole solve -- L-
 strong-Wolfe line search, projections, statistics -- runs device-resident through
 `mde_solver_*` (include/mde_b200.h); X is updated in place and returned."""
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -40,10 +41,16 @@ class SolveStats(object):
         p.text(self.__str__())
 
 
+# 1 = device-driven iterations (one CUDA graph per iteration: IF node for the fresh evaluation, WHILE node
+# for the line-search trials, scalars never leave the device); 0 = host-stepped line search (one 32-byte
+# status read per trial).  Edge-sharded multi-GPU solves use 0 (the NCCL hook is called from the host).
+DEFAULT_MODE = int(os.environ.get("PYMDE_B200_SOLVER_MODE", "1"))
+
+
 class DeviceSolver(object):
     """Owner of one `mde_solver_t`."""
 
-    def __init__(self, layout, n, m, constraint, memory_size, max_iter, world_size=1, allreduce=None):
+    def __init__(self, layout, n, m, constraint, memory_size, max_iter, world_size=1, allreduce=None, mode=None):
         lib = _lib.load()
         self.lib = lib
         self.layout = layout  # keep the edge layout alive
@@ -53,8 +60,9 @@ class DeviceSolver(object):
         opts.constraint = int(constraint._solver_id)
         opts.memory_size = int(memory_size)
         opts.max_iter = max(int(max_iter), 1)
-        opts.mode = 0
+        opts.mode = (DEFAULT_MODE if mode is None else int(mode)) if int(world_size) == 1 else 0
         opts.world_size = int(world_size)
+        self.mode = opts.mode
         self._keep = []
         if opts.constraint == _lib.CONSTRAINT_ANCHORED:
             anchors = constraint.anchors.to(device=self.device, dtype=torch.int64).contiguous()

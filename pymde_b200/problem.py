@@ -260,7 +260,7 @@ class MDE(torch.nn.Module):
         return 1 <= int(memory_size) <= 32
 
     def _solver(self, constraint, memory_size, max_iter):
-        key = (id(constraint), int(memory_size), int(max_iter))
+        key = (id(constraint), int(memory_size), int(max_iter), optim.DEFAULT_MODE)
         cur = self.__dict__["_device_solver"]
         if cur is None or cur[0] != key:
             if cur is not None:

@@ -28,8 +28,18 @@ def build(pm, key, g):
     return pm.MDE(n, m, torch.tensor(g[key + "/edges"], device="cuda"), f(), c), X0
 
 
+@pytest.fixture(params=[1, 0], ids=["graph", "hoststep"])
+def solver_mode(request):
+    """Run with the device-driven CUDA-graph solver (1) and the host-stepped one (0)."""
+    from pymde_b200 import optim
+    old = optim.DEFAULT_MODE
+    optim.DEFAULT_MODE = request.param
+    yield request.param
+    optim.DEFAULT_MODE = old
+
+
 @pytest.mark.parametrize("key", TRAJ)
-def test_embed_follows_reference_trajectory(golden, key):
+def test_embed_follows_reference_trajectory(golden, key, solver_mode):
     import pymde_b200 as pm
     g = golden["trajectories"]
     mde, X0 = build(pm, key, g)
@@ -86,8 +96,28 @@ def _knn_problem(pm, n, k, m, seed, constraint):
     return pm.MDE(n, m, torch.tensor(edges, device="cuda"), f, constraint), edges, w
 
 
+def test_graph_and_hoststep_modes_agree_bitwise():
+    """Both drivers enqueue the same kernels with the same fixed-order reductions; on a problem
+    evaluated without atomics races mattering (tiny, one block) the statistics must be identical."""
+    import pymde_b200 as pm
+    from pymde_b200 import optim
+    g = dict(np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "trajectories.npz")))
+    res = []
+    old = optim.DEFAULT_MODE
+    try:
+        for mode in (0, 1):
+            optim.DEFAULT_MODE = mode
+            mde, X0 = build(pm, "docs5", g)
+            mde.embed(X=X0, max_iter=30, eps=1e-7)
+            res.append((mde.solve_stats.iterations, list(mde.solve_stats.average_distortions)))
+    finally:
+        optim.DEFAULT_MODE = old
+    assert res[0][0] == res[1][0]
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-6)
+
+
 @pytest.mark.parametrize("cname", ["centered", "standardized"])
-def test_embed_invariants_medium(cname):
+def test_embed_invariants_medium(cname, solver_mode):
     import pymde_b200 as pm
     cons = pm.Centered() if cname == "centered" else pm.Standardized()
     n, m = 20000, 2
