@@ -20,6 +20,7 @@
 //    the one left by the LAST trial of iteration k's line search, the loss is the ACCEPTED
 //    trial's loss.
 #include <cstddef>
+#include <cstdlib>
 #include <new>
 
 #include "mde_common.cuh"
@@ -63,6 +64,7 @@ struct SolverState {
   float gtd;       // g.d
   float dmax;      // max |d|
   double dd, xx;   // ||d||^2, ||X||^2 at iteration start
+  unsigned int tickets[4];   // last-block-done counters of the fused vector+scalar kernels
   float mu_x[4], mu_d[4];  // column means of x_init and d (Centered, m in {1,2,4}: fused into the trial axpy)
   double t_last;   // state["t"]
   double t_eval;   // step of the most recent trial evaluation
@@ -83,11 +85,11 @@ __device__ void reduce_partials(const double* __restrict__ part, int nb, int K, 
   for (int k = w; k < K; k += nw) {
     double s = 0.0;
     if (MAXLAST && k == K - 1) {
-      for (int b = lane; b < nb; b += 32) s = fmax(s, part[(int64_t)b * K + k]);
+      for (int b = lane; b < nb; b += 32) s = fmax(s, __ldcg(part + (int64_t)b * K + k));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(kFull, s, o));
     } else {
-      for (int b = lane; b < nb; b += 32) s += part[(int64_t)b * K + k];
+      for (int b = lane; b < nb; b += 32) s += __ldcg(part + (int64_t)b * K + k);
       s = warp_sum(s);
     }
     if (lane == 0) out[k] = s;
@@ -95,17 +97,63 @@ __device__ void reduce_partials(const double* __restrict__ part, int nb, int K, 
   __syncthreads();
 }
 
+// "Last block done": every block publishes its partials, takes a ticket, and the block that draws the
+// last ticket runs the scalar epilogue in the same launch (saves one dependent launch per reduction).
+// The epilogue reads the partials in a fixed order, so the result does not depend on which block is last.
+__device__ bool last_block_done(unsigned int* counter) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == total - 1u) ? 1 : 0;
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+struct Tail {              // what a fused scalar epilogue needs
+  int fuse;                // 0: separate scalar kernel follows; 1: run the epilogue in the last block
+  int mode;                // grad_dots: 1 = line-search update, 2 = fresh evaluation
+  const double* lpart;     // loss partials of the distortion launch
+  int nl;
+  const float* tail;       // (hi, lo) of the all-reduced loss (multi-GPU)
+  double p_total;
+  int64_t n_rows;
+  cudaGraphConditionalHandle h_while;
+};
+
+__device__ void direction_scalar_body(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks,
+                                      unsigned char* smem);
+__device__ void ls_init_body(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks,
+                             int64_t n_rows, cudaGraphConditionalHandle h_while);
+__device__ void ls_update_body(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
+                               const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
+                               double p_total, cudaGraphConditionalHandle h_while);
+__device__ void fresh_finish_body(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
+                                  const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
+                                  double p_total);
+__device__ void iter_end_body(SolverState* __restrict__ S);
+
+constexpr int kScalarSmemBytes = (int)(sizeof(double) * (kMaxSlices * kDotsPerSlice + 5 * kSlots) + 64 + sizeof(LbfgsState));
+
 // ---------------------------------------------------------------------------------------
 // P1: candidate pair + all dot products of the history against (y_c, s_c, g)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kVecThreads)
 lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, const float* __restrict__ gprev,
                   const float* __restrict__ d, float* __restrict__ Sb, float* __restrict__ Yb,
-                  int64_t npad, double* __restrict__ part) {
-  if (off(&S->active) || S->lb.n_iter == 0) return;
+                  int64_t npad, double* __restrict__ part, Tail tl) {
+  if (off(&S->active)) return;
+  __shared__ __align__(16) unsigned char raw[sizeof(float) * kDotsPerSlice * kVecThreads];
+  static_assert(sizeof(raw) >= kScalarSmemBytes, "scalar epilogue must fit in the reduction tile");
   const int slice = blockIdx.y;
   const int count = S->lb.count;
-  if (slice > 0 && slice * kPairsPerSlice >= count) return;
+  const bool skip = (S->lb.n_iter == 0) || (slice > 0 && slice * kPairsPerSlice >= count);
+  if (!skip) {
   const float t = (float)S->t_last;
   float* sc = Sb + (int64_t)S->lb.cand * npad;
   float* yc = Yb + (int64_t)S->lb.cand * npad;
@@ -173,7 +221,7 @@ lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, cons
   // block reduction through a transposed shared-memory tile: 44 x 256 fp32 partials, then each
   // warp sums whole rows in fp64 (8 conflict-free loads per lane + one shuffle tree per row).
   // ~10x fewer instructions than 44 independent shuffle trees per thread.
-  __shared__ float tile[kDotsPerSlice][kVecThreads];
+  float (*tile)[kVecThreads] = reinterpret_cast<float (*)[kVecThreads]>(raw);
 #pragma unroll
   for (int k = 0; k < kDotsPerSlice; ++k) tile[k][threadIdx.x] = (float)dacc[k];
   __syncthreads();
@@ -188,6 +236,8 @@ lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, cons
       if (lane == 0) o[k] = sum;
     }
   }
+  }  // !skip
+  if (tl.fuse && last_block_done(&S->tickets[0])) direction_scalar_body(S, part, gridDim.x, raw);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -284,13 +334,13 @@ __device__ void lbfgs_direction_block(LbfgsState& B, double* dots, double ys, do
   }
 }
 
-__global__ void __launch_bounds__(256)
-direction_scalar_kernel(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks) {
-  if (off(&S->active)) return;
-  __shared__ double sums[kMaxSlices * kDotsPerSlice];
-  __shared__ double dots[5 * kSlots];
-  __shared__ int flags[4];
-  __shared__ LbfgsState sB;  // the whole history state (Gram matrices included) staged in shared memory
+__device__ void direction_scalar_body(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks,
+                                      unsigned char* smem) {
+  // carve: history state (Gram matrices included) | block sums | per-pair dots | flags
+  LbfgsState& sB = *reinterpret_cast<LbfgsState*>(smem);
+  double* sums = reinterpret_cast<double*>(smem + sizeof(LbfgsState));
+  double* dots = sums + kMaxSlices * kDotsPerSlice;
+  int* flags = reinterpret_cast<int*>(dots + 5 * kSlots);
   static_assert(sizeof(LbfgsState) % sizeof(double) == 0, "LbfgsState must be a whole number of doubles");
   static_assert(kMaxMemory <= 32, "the two-loop recursion maps one pair per lane");
   {
@@ -333,14 +383,21 @@ direction_scalar_kernel(SolverState* __restrict__ S, const double* __restrict__ 
   }
 }
 
+__global__ void __launch_bounds__(256)
+direction_scalar_kernel(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks) {
+  if (off(&S->active)) return;
+  __shared__ __align__(16) unsigned char raw[kScalarSmemBytes];
+  direction_scalar_body(S, part, nblocks, raw);
+}
+
 // ---------------------------------------------------------------------------------------
 // P2: d = cg*g + sum_j cs_j S_j + cy_j Y_j ; g_prev = g ; x_init = X ; partial g.d, d.d, X.X, max|d|
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kVecThreads)
-direction_apply_kernel(const SolverState* __restrict__ S, const float* __restrict__ g, float* __restrict__ gprev,
+direction_apply_kernel(SolverState* __restrict__ S, const float* __restrict__ g, float* __restrict__ gprev,
                        float* __restrict__ d, const float* __restrict__ X, float* __restrict__ xinit,
                        const float* __restrict__ Sb, const float* __restrict__ Yb, int64_t npad,
-                       double* __restrict__ part, int mcols) {
+                       double* __restrict__ part, int mcols, Tail tl) {
   if (off(&S->active)) return;
   __shared__ float cs[kMaxMemory], cy[kMaxMemory];
   __shared__ const float* ps[kMaxMemory];
@@ -412,13 +469,12 @@ direction_apply_kernel(const SolverState* __restrict__ S, const float* __restric
     for (int k = 0; k < KA; ++k) o[k] = acc[k];
     o[KA] = (double)m2;
   }
+  if (tl.fuse && last_block_done(&S->tickets[1])) ls_init_body(S, part, gridDim.x, tl.n_rows, tl.h_while);
 }
 
 // S2: finalize g.d, |d|, |X|; initial step; arm the line search (lbfgs.py:521-549)
-__global__ void __launch_bounds__(256)
-ls_init_kernel(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks, int64_t n_rows,
-               cudaGraphConditionalHandle h_while) {
-  if (off(&S->active)) return;
+__device__ void ls_init_body(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks,
+                             int64_t n_rows, cudaGraphConditionalHandle h_while) {
   __shared__ double out[12];
   reduce_partials<true>(part, nblocks, 12, out);
   if (threadIdx.x == 0) {
@@ -439,6 +495,13 @@ ls_init_kernel(SolverState* __restrict__ S, const double* __restrict__ part, int
   }
 }
 
+__global__ void __launch_bounds__(256)
+ls_init_kernel(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks, int64_t n_rows,
+               cudaGraphConditionalHandle h_while) {
+  if (off(&S->active)) return;
+  ls_init_body(S, part, nblocks, n_rows, h_while);
+}
+
 // graph mode: gate of the IF node around the fresh evaluation
 __global__ void fresh_gate_kernel(const SolverState* __restrict__ S, cudaGraphConditionalHandle h_if) {
   if (threadIdx.x == 0) cudaGraphSetConditional(h_if, (S->active && S->need_fresh) ? 1u : 0u);
@@ -454,7 +517,8 @@ __global__ void fresh_gate_kernel(const SolverState* __restrict__ S, cudaGraphCo
 template <bool FINAL>
 __global__ void __launch_bounds__(kVecThreads)
 trial_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, const float* __restrict__ d,
-                  float* __restrict__ X, int64_t npad, int64_t nvalid, int center_m, float* __restrict__ gz) {
+                  float* __restrict__ X, int64_t npad, int64_t nvalid, int center_m, float* __restrict__ gz,
+                  int fuse_end) {
   if (off(&S->active)) return;
   if (!FINAL && off(&S->ls_active)) return;
   const float t = FINAL ? (float)S->ls.t_accept : (float)S->ls.t;
@@ -485,6 +549,7 @@ trial_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, 
     }
     if (!FINAL && gz != nullptr) reinterpret_cast<float4*>(gz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (FINAL && fuse_end && last_block_done(&S->tickets[3])) iter_end_body(S);
 }
 
 __global__ void __launch_bounds__(kVecThreads)
@@ -521,7 +586,7 @@ pack_loss_kernel(const int* flag, const double* __restrict__ lpart, int nl, floa
 // T5: partial g.d, g.g, |g|_1
 __global__ void __launch_bounds__(kVecThreads)
 grad_dots_kernel(const int* flag, const float* __restrict__ g, const float* __restrict__ d, int64_t npad,
-                 double* __restrict__ part) {
+                 double* __restrict__ part, SolverState* __restrict__ S, Tail tl) {
   if (off(flag)) return;
   double acc[3] = {0.0, 0.0, 0.0};
   float fa[3] = {0.0f, 0.0f, 0.0f};
@@ -546,6 +611,10 @@ grad_dots_kernel(const int* flag, const float* __restrict__ g, const float* __re
     double* o = part + (int64_t)blockIdx.x * 3;
     o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
   }
+  if (tl.fuse && last_block_done(&S->tickets[2])) {
+    if (tl.mode == 1) ls_update_body(S, tl.lpart, tl.nl, tl.tail, part, gridDim.x, tl.p_total, tl.h_while);
+    else fresh_finish_body(S, tl.lpart, tl.nl, tl.tail, part, gridDim.x, tl.p_total);
+  }
 }
 
 // loss of one evaluation as the reference sees it: fp32 mean, then float(...)
@@ -563,10 +632,9 @@ __device__ double eval_loss(const SolverState* S, const double* lpart, int nl, c
 }
 
 // S(fresh): closure() at the current iterate (lbfgs.py:426), no line search involved
-__global__ void __launch_bounds__(256)
-fresh_finish_kernel(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
-                    const float* __restrict__ tail, const double* __restrict__ dpart, int nd, double p_total) {
-  if (off(&S->active) || off(&S->need_fresh)) return;
+__device__ void fresh_finish_body(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
+                                  const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
+                                  double p_total) {
   __shared__ double out[3];
   __shared__ double l1[1];
   double loss = eval_loss(S, lpart, nl, tail, l1, p_total);
@@ -578,15 +646,17 @@ fresh_finish_kernel(SolverState* __restrict__ S, const double* __restrict__ lpar
   }
 }
 
-// S(trial): feed (f_new, g.d) to the Wolfe state machine; decide the next step or finish
 __global__ void __launch_bounds__(256)
-ls_update_kernel(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
-                 const float* __restrict__ tail, const double* __restrict__ dpart, int nd, double p_total,
-                 cudaGraphConditionalHandle h_while) {
-  if (off(&S->active) || off(&S->ls_active)) {
-    if (h_while && threadIdx.x == 0) cudaGraphSetConditional(h_while, 0u);
-    return;
-  }
+fresh_finish_kernel(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
+                    const float* __restrict__ tail, const double* __restrict__ dpart, int nd, double p_total) {
+  if (off(&S->active) || off(&S->need_fresh)) return;
+  fresh_finish_body(S, lpart, nl, tail, dpart, nd, p_total);
+}
+
+// S(trial): feed (f_new, g.d) to the Wolfe state machine; decide the next step or finish
+__device__ void ls_update_body(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
+                               const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
+                               double p_total, cudaGraphConditionalHandle h_while) {
   __shared__ double out[3];
   __shared__ double l1[1];
   double loss = eval_loss(S, lpart, nl, tail, l1, p_total);
@@ -610,9 +680,19 @@ ls_update_kernel(SolverState* __restrict__ S, const double* __restrict__ lpart, 
   }
 }
 
+__global__ void __launch_bounds__(256)
+ls_update_kernel(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
+                 const float* __restrict__ tail, const double* __restrict__ dpart, int nd, double p_total,
+                 cudaGraphConditionalHandle h_while) {
+  if (off(&S->active) || off(&S->ls_active)) {
+    if (h_while && threadIdx.x == 0) cudaGraphSetConditional(h_while, 0u);
+    return;
+  }
+  ls_update_body(S, lpart, nl, tail, dpart, nd, p_total, h_while);
+}
+
 // S5: end of iteration (optim.py:135-173)
-__global__ void iter_end_kernel(SolverState* __restrict__ S) {
-  if (off(&S->active)) return;
+__device__ void iter_end_body(SolverState* __restrict__ S) {
   if (threadIdx.x != 0) return;
   const int it = S->iter;
   const double h = S->ls.t_accept;
@@ -626,6 +706,11 @@ __global__ void iter_end_kernel(SolverState* __restrict__ S) {
   if (S->iter >= S->max_stats) S->active = 0;
 }
 
+__global__ void iter_end_kernel(SolverState* __restrict__ S) {
+  if (off(&S->active)) return;
+  iter_end_body(S);
+}
+
 __global__ void init_state_kernel(SolverState* S, double eps, int memory, int max_stats, int world,
                                   double* avg, double* resid, double* pct, double* steplen) {
   if (threadIdx.x != 0) return;
@@ -633,6 +718,7 @@ __global__ void init_state_kernel(SolverState* S, double eps, int memory, int ma
   S->stop_after = 0; S->pad0 = 0; S->eps = eps; S->loss = 0.0; S->gg = 0.0; S->g1 = 0.0; S->gtd = 0.0f;
   S->dmax = 0.0f; S->dd = 0.0; S->xx = 0.0; S->t_last = 0.0; S->t_eval = 0.0; S->func_evals = 0;
   S->max_stats = max_stats; S->world = world;
+  for (int k = 0; k < 4; ++k) S->tickets[k] = 0u;
   S->avg = avg; S->resid = resid; S->pct = pct; S->steplen = steplen;
   lbfgs_reset(S->lb, memory);
   ls_begin(S->ls, 0.0, 0.0, 0.0f, 0.0f);
@@ -660,6 +746,7 @@ struct mde_solver {
   double *stats = nullptr;           // 4 * max_iter doubles
   void* projws = nullptr;
   ProjWs pw{};
+  int fuse = 1;                      // scalar epilogues run in the last block of the vector kernels
   int center_m = 0;                  // {1,2,4}: Centered projection fused into the trial axpy
   int nl = 0;                        // loss-partial blocks of the distortion launch
   int nvb = 0;                       // vector-pass blocks
@@ -708,7 +795,15 @@ int enqueue_project(mde_solver* s, cudaStream_t st) {
 }
 
 // closure: value_and_grad at s->X (optim.py:100-105); `flag` gates the kernels
-int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, cudaStream_t st) {
+Tail make_tail(mde_solver* s, int mode) {
+  Tail tl;
+  tl.fuse = s->fuse; tl.mode = mode;
+  tl.lpart = loss_partials_ptr(s->edges); tl.nl = s->nl; tl.tail = s->g + s->npad;
+  tl.p_total = (double)edges_p_total(s->edges); tl.n_rows = s->n; tl.h_while = s->h_while;
+  return tl;
+}
+
+int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cudaStream_t st) {
   if (zero_g) {
     const int64_t n4 = (s->npad + 4) >> 2;  // gradient + (hi, lo) tail
     zero_kernel<<<vec_blocks(n4), kVecThreads, 0, st>>>(flag, s->g, n4);
@@ -735,55 +830,70 @@ int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, cudaStream_t st) {
       MDE_LAUNCH_CHECK();
     }
   }
-  grad_dots_kernel<<<s->nvb, kVecThreads, 0, st>>>(flag, s->g, s->d, s->npad, s->dpart);
+  Tail tl = make_tail(s, tail_mode);
+  grad_dots_kernel<<<s->nvb, kVecThreads, 0, st>>>(flag, s->g, s->d, s->npad, s->dpart, s->S, tl);
   MDE_LAUNCH_CHECK();
   return 0;
 }
 
 int enqueue_fresh(mde_solver* s, cudaStream_t st) {
-  int rc = enqueue_eval(s, &s->S->need_fresh, true, st);
+  int rc = enqueue_eval(s, &s->S->need_fresh, true, 2, st);
   if (rc) return rc;
-  fresh_finish_kernel<<<1, 256, 0, st>>>(s->S, loss_partials_ptr(s->edges), s->nl, s->g + s->npad, s->dpart,
-                                         s->nvb, (double)edges_p_total(s->edges));
-  MDE_LAUNCH_CHECK();
+  if (!s->fuse) {
+    fresh_finish_kernel<<<1, 256, 0, st>>>(s->S, loss_partials_ptr(s->edges), s->nl, s->g + s->npad, s->dpart,
+                                           s->nvb, (double)edges_p_total(s->edges));
+    MDE_LAUNCH_CHECK();
+  }
   return 0;
 }
 
 int enqueue_direction(mde_solver* s, cudaStream_t st) {
   int slices = (s->opts.memory_size + kPairsPerSlice - 1) / kPairsPerSlice;
   dim3 grid(s->nvb, slices);
-  lbfgs_dots_kernel<<<grid, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->Sb, s->Yb, s->npad, s->dpart);
+  Tail tl = make_tail(s, 0);
+  lbfgs_dots_kernel<<<grid, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->Sb, s->Yb, s->npad, s->dpart, tl);
   MDE_LAUNCH_CHECK();
-  direction_scalar_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb);
-  MDE_LAUNCH_CHECK();
+  if (!s->fuse) {
+    direction_scalar_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb);
+    MDE_LAUNCH_CHECK();
+  }
   direction_apply_kernel<<<s->nvb, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->X, s->xinit, s->Sb,
-                                                         s->Yb, s->npad, s->dpart, s->center_m);
+                                                         s->Yb, s->npad, s->dpart, s->center_m, tl);
   MDE_LAUNCH_CHECK();
-  ls_init_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb, s->n, s->h_while);
-  MDE_LAUNCH_CHECK();
+  if (!s->fuse) {
+    ls_init_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb, s->n, s->h_while);
+    MDE_LAUNCH_CHECK();
+  }
   return 0;
 }
 
 int enqueue_trial(mde_solver* s, cudaStream_t st) {
-  trial_axpy_kernel<false><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, s->g);
+  trial_axpy_kernel<false><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, s->g, 0);
   MDE_LAUNCH_CHECK();
   int rc = enqueue_project(s, st);
   if (rc) return rc;
-  rc = enqueue_eval(s, &s->S->ls_active, false, st);
+  rc = enqueue_eval(s, &s->S->ls_active, false, 1, st);
   if (rc) return rc;
-  ls_update_kernel<<<1, 256, 0, st>>>(s->S, loss_partials_ptr(s->edges), s->nl, s->g + s->npad, s->dpart, s->nvb,
-                                      (double)edges_p_total(s->edges), s->h_while);
-  MDE_LAUNCH_CHECK();
+  if (!s->fuse) {
+    ls_update_kernel<<<1, 256, 0, st>>>(s->S, loss_partials_ptr(s->edges), s->nl, s->g + s->npad, s->dpart, s->nvb,
+                                        (double)edges_p_total(s->edges), s->h_while);
+    MDE_LAUNCH_CHECK();
+  }
   return 0;
 }
 
 int enqueue_finish(mde_solver* s, cudaStream_t st) {
-  trial_axpy_kernel<true><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, nullptr);
+  // iter_end may ride in the axpy's last block only when no projection kernel follows (it can clear `active`)
+  const int fuse_end = (s->fuse && s->opts.constraint == MDE_CONSTRAINT_CENTERED && s->center_m) ? 1 : 0;
+  trial_axpy_kernel<true><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m,
+                                                          nullptr, fuse_end);
   MDE_LAUNCH_CHECK();
   int rc = enqueue_project(s, st);
   if (rc) return rc;
-  iter_end_kernel<<<1, 32, 0, st>>>(s->S);
-  MDE_LAUNCH_CHECK();
+  if (!fuse_end) {
+    iter_end_kernel<<<1, 32, 0, st>>>(s->S);
+    MDE_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -905,6 +1015,7 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   }
   s->nvb = vec_blocks(s->npad >> 2);
   if (opts->constraint == MDE_CONSTRAINT_CENTERED && (m == 1 || m == 2 || m == 4)) s->center_m = m;
+  { const char* ev = getenv("MDE_B200_FUSE"); if (ev && ev[0] == '0') s->fuse = 0; }
   if (opts->mode == 1) {
     s->nl = 0;
     TRY(cudaStreamSynchronize(st));
