@@ -15,10 +15,13 @@ from .util import align, all_edges, center, seed  # noqa: F401
 
 def __getattr__(name):
     # recipes / preprocessing import scipy & sklearn; load them on first use
+    import importlib
     if name in ("preserve_neighbors", "preserve_distances", "laplacian_embedding", "recipes"):
-        from . import recipes
+        recipes = importlib.import_module(__name__ + ".recipes")
         return recipes if name == "recipes" else getattr(recipes, name)
     if name in ("preprocess", "Graph"):
-        from . import preprocess
+        preprocess = importlib.import_module(__name__ + ".preprocess")
         return preprocess if name == "preprocess" else preprocess.Graph
+    if name == "quadratic":
+        return importlib.import_module(__name__ + ".quadratic")
     raise AttributeError("module 'pymde_b200' has no attribute %r" % name)

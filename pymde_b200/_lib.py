@@ -41,6 +41,8 @@ SIGNATURES = {
     "mde_launch_count": (C.c_uint64, []),
     "mde_edges_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                    C.c_void_p, C.POINTER(mde_fn_t), C.c_int64, C.c_void_p]),
+    "mde_edges_create_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.POINTER(mde_fn_t), C.c_int64, C.c_int, C.c_void_p]),
     "mde_edges_destroy": (C.c_int, [C.c_void_p]),
     "mde_edges_count": (C.c_int64, [C.c_void_p]),
     "mde_edges_nbytes": (C.c_int64, [C.c_void_p]),

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 
 #include "mde_common.cuh"
 
@@ -38,6 +39,7 @@ struct mde_edges {
   double* loss_partials = nullptr;  // [kMaxLossBlocks]
   FnDev fn;
   int has_par1 = 0;
+  int tiled = 0;  // edge order grouped into L2-sized (src_tile, dst_tile) buckets
   int64_t nbytes = 0;
 };
 
@@ -58,6 +60,30 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ edges, const float*
   uint64_t cls = (push_pull && !(par0[k] >= 0.0f)) ? 1ull : 0ull;
   keys[k] = (cls << 63) | (lo << 32) | hi;  // n < 2^31
   vals[k] = (int32_t)k;
+}
+
+// Second-level key for large graphs: (class, src_tile, dst_tile).  A stable sort on it after the
+// (class, src, dst) sort groups the edges into tile-pair buckets whose vertex rows (X and gradient of
+// both tiles) fit in the 126 MB L2, so the random gathers / reds of a bucket hit L2 instead of HBM.
+__global__ void tile_keys_kernel(const uint64_t* __restrict__ keys, int64_t p, int64_t tile_rows,
+                                 uint32_t* __restrict__ tkeys, int32_t* __restrict__ idx) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p) return;
+  const uint64_t key = keys[k];
+  const uint32_t cls = (uint32_t)(key >> 63);
+  const uint32_t s = (uint32_t)((key >> 32) & 0x7fffffffu), d = (uint32_t)(key & 0xffffffffu);
+  tkeys[k] = (cls << 16) | ((uint32_t)(s / tile_rows) << 8) | (uint32_t)(d / tile_rows);
+  idx[k] = (int32_t)k;
+}
+
+__global__ void gather_sorted_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
+                                     const int32_t* __restrict__ order, int64_t p, uint64_t* __restrict__ keys2,
+                                     int32_t* __restrict__ vals2) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p) return;
+  const int32_t o = order[k];
+  keys2[k] = keys[o];
+  vals2[k] = vals[o];
 }
 
 __global__ void unpack_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
@@ -199,7 +225,7 @@ distortion_small_kernel(const int32_t* __restrict__ src, const int32_t* __restri
 // ------------------------------------------------------------------------------------------
 static constexpr int kQuadThreads = 256;
 
-template <int M, int MODE, int FA, int FR, bool FAST>
+template <int M, int MODE, int FA, int FR, bool FAST, int NQ>
 __global__ void __launch_bounds__(kQuadThreads)
 distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                        const float* __restrict__ par0, const float* __restrict__ par1,
@@ -208,37 +234,46 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
                        double* __restrict__ loss_partials, FnDev fn, float inv_p,
                        const int* __restrict__ flag) {
   if (flag != nullptr && *flag == 0) return;
+  constexpr int E = 4 * NQ;  // consecutive edges owned by a thread per iteration
   const int64_t nquads = (p + 3) >> 2;
+  const int64_t nunits = (nquads + NQ - 1) / NQ;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float lsum_f = 0.0f;
   double lsum = 0.0;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
-    const int4 s4 = __ldg(reinterpret_cast<const int4*>(src) + q);
-    const int4 t4 = __ldg(reinterpret_cast<const int4*>(dst) + q);
-    int s[4] = {s4.x, s4.y, s4.z, s4.w};
-    int t[4] = {t4.x, t4.y, t4.z, t4.w};
-    float a[4], b[4];
-    if (MODE == 2) {
-      const int4 o4 = __ldg(reinterpret_cast<const int4*>(perm) + q);  // pad entries repeat the last edge
-      a[0] = __ldg(gext + o4.x); a[1] = __ldg(gext + o4.y); a[2] = __ldg(gext + o4.z); a[3] = __ldg(gext + o4.w);
-    } else {
-      const float4 a4 = __ldg(reinterpret_cast<const float4*>(par0) + q);
-      a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
-    }
-    if (MODE != 2 && par1 != nullptr) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(par1) + q);
-      b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
-    } else { b[0] = b[1] = b[2] = b[3] = 0.0f; }
-    Row<M> xi[4], xj[4];
+  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nunits; u += stride) {
+    int s[E], t[E];
+    float a[E], b[E];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { xi[e] = load_row<M>(X, s[e]); xj[e] = load_row<M>(X, t[e]); }
+    for (int j = 0; j < NQ; ++j) {
+      const int64_t q = u * NQ + j;
+      const int64_t qc = q < nquads ? q : nquads - 1;  // clamped: masked below through `ok`
+      const int4 s4 = __ldg(reinterpret_cast<const int4*>(src) + qc);
+      const int4 t4 = __ldg(reinterpret_cast<const int4*>(dst) + qc);
+      s[4 * j] = s4.x; s[4 * j + 1] = s4.y; s[4 * j + 2] = s4.z; s[4 * j + 3] = s4.w;
+      t[4 * j] = t4.x; t[4 * j + 1] = t4.y; t[4 * j + 2] = t4.z; t[4 * j + 3] = t4.w;
+      if (MODE == 2) {
+        const int4 o4 = __ldg(reinterpret_cast<const int4*>(perm) + qc);  // pad entries repeat the last edge
+        a[4 * j] = __ldg(gext + o4.x); a[4 * j + 1] = __ldg(gext + o4.y);
+        a[4 * j + 2] = __ldg(gext + o4.z); a[4 * j + 3] = __ldg(gext + o4.w);
+      } else {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(par0) + qc);
+        a[4 * j] = a4.x; a[4 * j + 1] = a4.y; a[4 * j + 2] = a4.z; a[4 * j + 3] = a4.w;
+      }
+      if (MODE != 2 && par1 != nullptr) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(par1) + qc);
+        b[4 * j] = b4.x; b[4 * j + 1] = b4.y; b[4 * j + 2] = b4.z; b[4 * j + 3] = b4.w;
+      } else { b[4 * j] = b[4 * j + 1] = b[4 * j + 2] = b[4 * j + 3] = 0.0f; }
+    }
+    Row<M> xi[E], xj[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { xi[e] = load_row<M>(X, s[e]); xj[e] = load_row<M>(X, t[e]); }
     float acc[M];
 #pragma unroll
     for (int c = 0; c < M; ++c) acc[c] = 0.0f;
     int cur = s[0];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const bool ok = (4 * q + e) < p;
+    for (int e = 0; e < E; ++e) {
+      const bool ok = (4 * (u * NQ) + e) < p;
       float diff[M];
       float d2 = 0.0f;
 #pragma unroll
@@ -468,8 +503,14 @@ int loss_blocks_small(int64_t p) {
   return (int)nb;
 }
 
-int loss_blocks_quad(int64_t p) {
-  int64_t per_block = (int64_t)kQuadThreads * 4;
+int quad_nq() {  // consecutive quads per thread: MDE_B200_NQ=1|2 (experimental A/B switch; default 1)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MDE_B200_NQ"); v = (e && e[0] == '2') ? 2 : 1; }
+  return v;
+}
+
+int loss_blocks_quad(int64_t p, int nq) {
+  int64_t per_block = (int64_t)kQuadThreads * 4 * nq;
   int64_t nb = (p + per_block - 1) / per_block;
   if (nb < 1) nb = 1;
   if (nb > kNumSMs * 8) nb = kNumSMs * 8;
@@ -509,13 +550,16 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
       e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
       e->loss_partials, e->fn, inv_p, flag)
   // hot function combinations get compile-time ids (fused mode, m = 2 / 3); the rest use the table
-#define QUADK(MM, FA, FR, FAST)                                                                       \
-  distortion_quad_kernel<MM, MODE, FA, FR, FAST><<<nb, kQuadThreads, 0, st>>>(                        \
+#define QUADK_(MM, FA, FR, FAST, NQV)                                                                 \
+  distortion_quad_kernel<MM, MODE, FA, FR, FAST, NQV><<<nb, kQuadThreads, 0, st>>>(                   \
       e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
       e->loss_partials, e->fn, inv_p, flag)
+#define QUADK(MM, FA, FR, FAST)                                                                       \
+  if (FAST && quad_nq() == 2) { nb = loss_blocks_quad(p, 2); QUADK_(MM, FA, FR, FAST, 2); }           \
+  else { nb = loss_blocks_quad(p, 1); QUADK_(MM, FA, FR, FAST, 1); }
 #define SMALL(MM)                                                                                     \
   if (small_kernel_variant() != 1) {                                                                  \
-    nb = loss_blocks_quad(p);                                                                         \
+    nb = loss_blocks_quad(p, 1);                                                                      \
     const int fa = e->fn.fn_att, fr = e->fn.fn_rep, pp = e->fn.push_pull;                             \
     const bool hot = pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOG && e->fn.a0 == 1.5f &&          \
                      e->fn.r0 == 1.0f && small_kernel_variant() == 0;                                 \
@@ -578,6 +622,7 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
 #undef SMALL
 #undef SMALL_STRIDED
 #undef QUADK
+#undef QUADK_
 #undef SMALLK
 #undef WIDE
   MDE_LAUNCH_CHECK();
@@ -620,6 +665,12 @@ const char* mde_error_string(int code) {
 int mde_edges_create(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t n_items,
                      const float* par0, const float* par1, const mde_fn_t* fn, int64_t p_total,
                      void* stream) {
+  return mde_edges_create_ex(out, edges, p, n_items, par0, par1, fn, p_total, 2, stream);
+}
+
+int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t n_items,
+                        const float* par0, const float* par1, const mde_fn_t* fn, int64_t p_total,
+                        int embedding_dim, void* stream) {
   if (!out || !edges || !par0 || !fn || p <= 0 || n_items <= 0 || p >= (1ll << 31) ||
       n_items >= (1ll << 31) || p_total < p)
     return MDE_E_INVALID;
@@ -653,6 +704,39 @@ int mde_edges_create(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t
     TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p, 0, 64, st));
     TRY(cudaMalloc(&tmp, tmp_bytes));
     TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p, 0, 64, st));
+    // L2 tiling: 4 tiles (X and gradient rows of the src and dst tile) should stay within ~48 MB
+    {
+      const char* ev = getenv("MDE_B200_TILE_ROWS");
+      const int md = embedding_dim > 0 ? embedding_dim : 2;
+      // Measured on B200 (profiles/r01_scale.md): at n = 1e7, p = 1e8 the kernel is bound by L2 sector
+      // operations (one random 32-byte gather + one random 32-byte red per edge), not by HBM misses, and
+      // the bucket order gains nothing (1.56 ms tiled vs 1.53 ms untiled).  Kept as an opt-in experiment:
+      // MDE_B200_TILE_ROWS=<rows> (e.g. 48 MB / (16 * m)).
+      (void)md;
+      int64_t tile_rows = ev ? atoll(ev) : 0;
+      if (tile_rows > 0 && n_items > tile_rows && (n_items + tile_rows - 1) / tile_rows <= 255) {
+        uint32_t *tk_in = nullptr, *tk_out = nullptr;
+        int32_t* ord_out = nullptr;
+        void* tmp2 = nullptr;
+        size_t tmp2_bytes = 0;
+        TRY(cudaMalloc(&tk_in, sizeof(uint32_t) * p));
+        TRY(cudaMalloc(&tk_out, sizeof(uint32_t) * p));
+        TRY(cudaMalloc(&ord_out, sizeof(int32_t) * p));
+        tile_keys_kernel<<<nb, tb, 0, st>>>(keys_out, p, tile_rows, tk_in, vals_in);
+        ++g_launch_count;
+        TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp2_bytes, tk_in, tk_out, vals_in, ord_out, (int)p, 0, 17, st));
+        TRY(cudaMalloc(&tmp2, tmp2_bytes));
+        TRY(cub::DeviceRadixSort::SortPairs(tmp2, tmp2_bytes, tk_in, tk_out, vals_in, ord_out, (int)p, 0, 17, st));
+        gather_sorted_kernel<<<nb, tb, 0, st>>>(keys_out, vals_out, ord_out, p, keys_in, vals_in);
+        ++g_launch_count;
+        TRY(cudaPeekAtLastError());
+        TRY(cudaStreamSynchronize(st));
+        std::swap(keys_in, keys_out);
+        std::swap(vals_in, vals_out);
+        cudaFree(tk_in); cudaFree(tk_out); cudaFree(ord_out); cudaFree(tmp2);
+        e->tiled = 1;
+      }
+    }
     unpack_kernel<<<ceil_div_i64(p + 4, tb), tb, 0, st>>>(keys_out, vals_out, par0, par1, p, e->src, e->dst, e->par0, e->par1);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());

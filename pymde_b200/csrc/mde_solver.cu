@@ -310,24 +310,34 @@ __device__ void lbfgs_direction_block(LbfgsState& B, double* dots, double ys, do
     if (tid == 0) { B.SY[h][h] = ys; B.YY[h][h] = yy; sj_g[h] = sc_g; yj_g[h] = yc_g; }
     __syncthreads();
   }
-  if (tid < 32) {  // two-loop recursion (lbfgs.py:488-507) on the Gram matrices
+  if (tid < 32) {
+    // Two-loop recursion (lbfgs.py:488-507) on the Gram matrices, written as two triangular
+    // substitutions in column-oriented form: lane k owns its own right-hand side, each step is one
+    // divide + one broadcast + one FMA (no per-step warp reduction).
+    //   loop 1 (newest -> oldest):  R al = -S^T g     with R = upper triangle of SY (s_i . y_j, j >= i)
+    //   loop 2 (oldest -> newest):  c_i = al_i - (H (Y^T q)_i + sum_{j<i} c_j SY[j][i]) / SY[i][i]
     const int lane = tid, h = B.count;
     const double H = B.H_diag;
-    double al = 0.0, cc = 0.0;
+    double rhs = (lane < h) ? -sj_g[lane] : 0.0;
+    double al = 0.0;
     for (int i = h - 1; i >= 0; --i) {
-      double term = (lane > i && lane < h) ? al * B.SY[i][lane] : 0.0;
-      double sq = -sj_g[i] - warp_sum(term);
-      double ali = sq / B.SY[i][i];
+      const double ali = __shfl_sync(kFull, rhs, i) / B.SY[i][i];
       if (lane == i) al = ali;
+      if (lane < i) rhs -= ali * B.SY[lane][i];
     }
-    for (int i = 0; i < h; ++i) {
-      double t1 = (lane < h) ? al * B.YY[i][lane] : 0.0;
-      double yq = -yj_g[i] - warp_sum(t1);
-      double t2 = (lane < i) ? cc * B.SY[lane][i] : 0.0;
-      double yr = H * yq + warp_sum(t2);
-      double be = yr / B.SY[i][i];
-      double ali = __shfl_sync(kFull, al, i);
-      if (lane == i) cc = ali - be;
+    // (Y^T q)_i = -y_i.g - sum_j al_j y_i.y_j : every lane needs all al_j
+    double yq = (lane < h) ? -yj_g[lane] : 0.0;
+    for (int j = 0; j < h; ++j) {
+      const double alj = __shfl_sync(kFull, al, j);
+      if (lane < h) yq -= alj * B.YY[lane][j];
+    }
+    double acc = H * yq, cc = 0.0;
+    for (int j = 0; j < h; ++j) {
+      const double accj = __shfl_sync(kFull, acc, j);
+      const double alj = __shfl_sync(kFull, al, j);
+      const double ccj = alj - accj / B.SY[j][j];
+      if (lane == j) cc = ccj;
+      if (lane > j && lane < h) acc += ccj * B.SY[j][lane];
     }
     if (lane < h) { B.cs[lane] = cc; B.cy[lane] = -H * al; }
     if (lane == 0) B.cg = -H;
@@ -522,6 +532,9 @@ trial_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, 
   if (off(&S->active)) return;
   if (!FINAL && off(&S->ls_active)) return;
   const float t = FINAL ? (float)S->ls.t_accept : (float)S->ls.t;
+  // FINAL: the accepted step is usually the last trial evaluated -- X already holds exactly
+  // project(x_init + t d) (same kernel, same inputs, deterministic), so only the epilogue is needed.
+  const bool same_point = FINAL && center_m != 0 && (S->ls.t_accept == S->t_eval);
   float mu[4] = {0.f, 0.f, 0.f, 0.f};
   if (center_m == 1) { float v = S->mu_x[0] + t * S->mu_d[0]; mu[0] = mu[1] = mu[2] = mu[3] = v; }
   else if (center_m == 2) {
@@ -533,7 +546,7 @@ trial_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, 
   }
   const int64_t n4 = npad >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + 1; i += stride) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + 1 && !same_point; i += stride) {
     if (i < n4) {
       float4 A = reinterpret_cast<const float4*>(xinit)[i];
       float4 D = reinterpret_cast<const float4*>(d)[i];

@@ -32,7 +32,7 @@ if not LOGGER.handlers:
 class EdgeLayout(object):
     """Owner of one `mde_edges_t` (device-resident sorted int32 COO + permuted parameters)."""
 
-    def __init__(self, edges, n_items, table, par0, par1, device, p_total=None):
+    def __init__(self, edges, n_items, table, par0, par1, device, p_total=None, embedding_dim=2):
         lib = _lib.load()
         self.lib = lib
         self.device = device
@@ -53,10 +53,10 @@ class EdgeLayout(object):
         handle = C.c_void_p()
         self.table = table
         with torch.cuda.device(device):
-            _lib.check(lib.mde_edges_create(C.byref(handle), e.data_ptr(), self.p, self.n, par0.data_ptr(),
-                                            None if p1 is None else p1.data_ptr(), C.byref(table),
-                                            int(self.p if p_total is None else p_total),
-                                            util.stream_ptr(device)))
+            _lib.check(lib.mde_edges_create_ex(C.byref(handle), e.data_ptr(), self.p, self.n, par0.data_ptr(),
+                                               None if p1 is None else p1.data_ptr(), C.byref(table),
+                                               int(self.p if p_total is None else p_total), int(embedding_dim),
+                                               util.stream_ptr(device)))
         self.handle = handle
         self.loss = torch.zeros(1, dtype=torch.float64, device=device)
         self.p_total = int(self.p if p_total is None else p_total)
@@ -242,7 +242,8 @@ class MDE(torch.nn.Module):
                 table.fn_att = table.fn_rep = 100
                 par0, par1 = torch.zeros(int(self.p), device=self.device), None
             p_total = None if self.__dict__["_dist"] is None else self.__dict__["_dist"]["p_total"]
-            lay = EdgeLayout(self.edges, int(self.n_items), table, par0, par1, self.device, p_total=p_total)
+            lay = EdgeLayout(self.edges, int(self.n_items), table, par0, par1, self.device, p_total=p_total,
+                             embedding_dim=int(self.embedding_dim))
             self.__dict__["_edge_layout"] = lay
         return lay
 
