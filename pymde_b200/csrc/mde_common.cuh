@@ -201,7 +201,7 @@ __device__ __forceinline__ void edge_value(const FnDev& fn, float d, float a, fl
 // ------------------------------------------------------------------------------------------
 // fast path for the recipe default PushAndPull(Log1p(1.5), Log(1.0)) (pymde/recipes.py:224-225):
 // MUFU approximations (rsqrt / sqrt / rcp / lg2 / ex2, <= 2 ulp each) instead of the IEEE
-// sequences.  The kernel is instruction-issue bound (profiles/r01_ncu_distortion.md), and only the
+// sequences.  The kernel is instruction-issue bound (profiles/r01_ncu_summary.md), and only the
 // SUM of the per-edge losses has to agree with the reference to 1e-5: a 1e-7 absolute error per edge
 // is far inside that.  Inputs: squared distance d2.  Outputs: f_k and g_k = f'_k / (p d).
 // ------------------------------------------------------------------------------------------

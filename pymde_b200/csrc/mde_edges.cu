@@ -708,7 +708,7 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
     {
       const char* ev = getenv("MDE_B200_TILE_ROWS");
       const int md = embedding_dim > 0 ? embedding_dim : 2;
-      // Measured on B200 (profiles/r01_scale.md): at n = 1e7, p = 1e8 the kernel is bound by L2 sector
+      // Measured on B200 (profiles/r01_ncu_summary.md section 2): at n = 1e7, p = 1e8 the kernel is bound by L2 sector
       // operations (one random 32-byte gather + one random 32-byte red per edge), not by HBM misses, and
       // the bucket order gains nothing (1.56 ms tiled vs 1.53 ms untiled).  Kept as an opt-in experiment:
       // MDE_B200_TILE_ROWS=<rows> (e.g. 48 MB / (16 * m)).

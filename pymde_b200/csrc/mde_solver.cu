@@ -78,21 +78,29 @@ struct SolverState {
 
 __device__ __forceinline__ bool off(const int* flag) { return *flag == 0; }
 
-// fixed-order reduction of K sums over nb block partials, into smem out[K]; all threads call
+// Fixed-order reduction of K sums over nb block partials into smem out[K]; all threads of the block call.
+// Thread t owns (k = t % K, segment = t / K) and walks blocks segment, segment + S, ... with independent,
+// coalesced loads (through L2: the partials may come from other SMs of the same launch); the S segment
+// sums of each k are then combined in a fixed order.  Deterministic for a given launch shape.
 template <bool MAXLAST>
 __device__ void reduce_partials(const double* __restrict__ part, int nb, int K, double* out) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int k = w; k < K; k += nw) {
+  __shared__ double red_buf[256];
+  const int T = blockDim.x < 256 ? blockDim.x : 256;
+  const int S = T / K;  // segments (K <= 44 < T)
+  const int k = threadIdx.x % K, seg = threadIdx.x / K;
+  const bool is_max = MAXLAST && (k == K - 1);
+  if (threadIdx.x < S * K) {
     double s = 0.0;
-    if (MAXLAST && k == K - 1) {
-      for (int b = lane; b < nb; b += 32) s = fmax(s, __ldcg(part + (int64_t)b * K + k));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(kFull, s, o));
-    } else {
-      for (int b = lane; b < nb; b += 32) s += __ldcg(part + (int64_t)b * K + k);
-      s = warp_sum(s);
-    }
-    if (lane == 0) out[k] = s;
+    if (is_max) { for (int b = seg; b < nb; b += S) s = fmax(s, __ldcg(part + (int64_t)b * K + k)); }
+    else { for (int b = seg; b < nb; b += S) s += __ldcg(part + (int64_t)b * K + k); }
+    red_buf[seg * K + k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    const bool mx = MAXLAST && (threadIdx.x == K - 1);
+    double s = 0.0;
+    for (int q = 0; q < S; ++q) { const double v = red_buf[q * K + threadIdx.x]; s = mx ? fmax(s, v) : s + v; }
+    out[threadIdx.x] = s;
   }
   __syncthreads();
 }
