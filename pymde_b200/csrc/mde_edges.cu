@@ -240,6 +240,19 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float lsum_f = 0.0f;
   double lsum = 0.0;
+  // software pipeline (NQ == 1): the edge record of the NEXT grid-stride iteration is requested before the
+  // vertex rows of the current one are gathered, so its latency overlaps the gathers and the math
+  int4 s4n = make_int4(0, 0, 0, 0), t4n = make_int4(0, 0, 0, 0);
+  float4 a4n = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool pipe = (NQ == 1 && MODE != 2);
+  {
+    const int64_t u0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pipe && u0 < nunits) {
+      s4n = __ldg(reinterpret_cast<const int4*>(src) + u0);
+      t4n = __ldg(reinterpret_cast<const int4*>(dst) + u0);
+      a4n = __ldg(reinterpret_cast<const float4*>(par0) + u0);
+    }
+  }
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nunits; u += stride) {
     int s[E], t[E];
     float a[E], b[E];
@@ -247,8 +260,18 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
     for (int j = 0; j < NQ; ++j) {
       const int64_t q = u * NQ + j;
       const int64_t qc = q < nquads ? q : nquads - 1;  // clamped: masked below through `ok`
-      const int4 s4 = __ldg(reinterpret_cast<const int4*>(src) + qc);
-      const int4 t4 = __ldg(reinterpret_cast<const int4*>(dst) + qc);
+      int4 s4, t4;
+      if (pipe) {
+        s4 = s4n; t4 = t4n;
+        const int64_t un = u + stride;
+        if (un < nunits) {
+          s4n = __ldg(reinterpret_cast<const int4*>(src) + un);
+          t4n = __ldg(reinterpret_cast<const int4*>(dst) + un);
+        }
+      } else {
+        s4 = __ldg(reinterpret_cast<const int4*>(src) + qc);
+        t4 = __ldg(reinterpret_cast<const int4*>(dst) + qc);
+      }
       s[4 * j] = s4.x; s[4 * j + 1] = s4.y; s[4 * j + 2] = s4.z; s[4 * j + 3] = s4.w;
       t[4 * j] = t4.x; t[4 * j + 1] = t4.y; t[4 * j + 2] = t4.z; t[4 * j + 3] = t4.w;
       if (MODE == 2) {
@@ -256,7 +279,14 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
         a[4 * j] = __ldg(gext + o4.x); a[4 * j + 1] = __ldg(gext + o4.y);
         a[4 * j + 2] = __ldg(gext + o4.z); a[4 * j + 3] = __ldg(gext + o4.w);
       } else {
-        const float4 a4 = __ldg(reinterpret_cast<const float4*>(par0) + qc);
+        float4 a4;
+        if (pipe) {
+          a4 = a4n;
+          const int64_t un = u + stride;
+          if (un < nunits) a4n = __ldg(reinterpret_cast<const float4*>(par0) + un);
+        } else {
+          a4 = __ldg(reinterpret_cast<const float4*>(par0) + qc);
+        }
         a[4 * j] = a4.x; a[4 * j + 1] = a4.y; a[4 * j + 2] = a4.z; a[4 * j + 3] = a4.w;
       }
       if (MODE != 2 && par1 != nullptr) {
@@ -509,11 +539,17 @@ int quad_nq() {  // consecutive quads per thread: MDE_B200_NQ=1|2 (experimental 
   return v;
 }
 
+int quad_grid_cap() {  // blocks per SM in the grid cap: MDE_B200_QUAD_BPS (default 4 = one resident wave)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MDE_B200_QUAD_BPS"); v = e ? atoi(e) : 4; if (v < 1) v = 1; if (v > 16) v = 16; }
+  return v;
+}
+
 int loss_blocks_quad(int64_t p, int nq) {
   int64_t per_block = (int64_t)kQuadThreads * 4 * nq;
   int64_t nb = (p + per_block - 1) / per_block;
   if (nb < 1) nb = 1;
-  if (nb > kNumSMs * 8) nb = kNumSMs * 8;
+  if (nb > kNumSMs * quad_grid_cap()) nb = kNumSMs * quad_grid_cap();
   return (int)nb;
 }
 

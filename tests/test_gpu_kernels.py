@@ -280,3 +280,27 @@ def test_external_callable_distortion_function():
     v_ref, g_ref = O.average_distortion(X.astype(np.float64), e, O.FnSpec(O.P_QUADRATIC, w), True)
     np.testing.assert_allclose(v.item(), v_ref, rtol=1e-5)
     np.testing.assert_allclose(Xt.grad.cpu().numpy(), g_ref, atol=2e-5 * float(np.abs(g_ref).max()))
+
+
+def test_full_size_c2_against_c_oracle():
+    """BASELINE config C2 at FULL size (n=70 000, m=2, p~1.55 M, PushAndPull(Log1p, Log)): value and gradient
+    of the fused kernel against the C restatement of the reference (oracle/mde_oracle.c, float64)."""
+    pm = _pm()
+    import bench
+    from oracle import c_oracle
+    edges, w = bench.c2_edges(0)
+    X0 = bench.initial_iterate(0)
+    spec = O.FnSpec(O.P_LOG1P, w, (1.5, 0, 0), fn_rep=O.P_LOG, rep=(1.0, 0, 0))
+    v_ref, g_ref = c_oracle.average_distortion(X0, edges, spec)
+    f = pm.penalties.PushAndPull(torch.tensor(w, device="cuda"), pm.penalties.Log1p, pm.penalties.Log)
+    mde = pm.MDE(bench.N_ITEMS, 2, torch.tensor(edges, device="cuda"), f)
+    X = torch.tensor(X0, device="cuda", requires_grad=True)
+    v = mde.average_distortion(X)
+    v.backward()
+    np.testing.assert_allclose(v.item(), v_ref, rtol=1e-5)  # north_star tolerance
+    np.testing.assert_allclose(X.grad.cpu().numpy(), g_ref, atol=2e-5 * np.abs(g_ref).max(), rtol=1e-3)
+    # bit-exact on edge indices: the caller's int64 list is untouched and per-edge outputs keep its order
+    assert torch.equal(mde.edges.cpu(), torch.tensor(edges))
+    d = mde.distances(X.detach()).cpu().numpy()
+    d_ref = np.linalg.norm(X0[edges[:, 0]].astype(np.float64) - X0[edges[:, 1]].astype(np.float64), axis=1)
+    np.testing.assert_allclose(d, d_ref, rtol=1e-5)
