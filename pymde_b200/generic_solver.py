@@ -129,7 +129,7 @@ def lbfgs_generic(X, objective_fn, constraint, eps, max_iter, memory_size, use_l
             g = constraint.project_onto_tangent_space(Xe.detach(), g, inplace=True)
         evals[0] += 1
         grad[0] = g
-        return float(v)
+        return float(v.detach())
 
     state = None
     cached = None

@@ -198,3 +198,40 @@ def test_custom_constraint_and_callable_use_generic_solver():
     mde2 = pm.MDE(n, m, torch.tensor(edges, device="cuda"), lambda d: wt * d.pow(2), pm.Centered())
     mde2.embed(max_iter=10)
     assert mde2.solve_stats.average_distortions[-1] < mde2.solve_stats.average_distortions[0]
+
+
+def test_solver_error_where_the_reference_raises():
+    """All items on one point with a repulsive Log penalty: the loss is +inf at every trial step, the line
+    search backs off 10 times and the reference raises SolverError (pymde/lbfgs.py:59-80)."""
+    import pymde_b200 as pm
+    n = 50
+    edges = pm.all_edges(n).cuda()
+    f = pm.penalties.Log(-torch.ones(edges.shape[0], device="cuda"))
+    mde = pm.MDE(n, 2, edges, f, pm.Centered())
+    with pytest.raises(pm.util.SolverError):
+        mde.embed(X=torch.zeros(n, 2, device="cuda"), max_iter=5)
+
+
+def test_wide_standardized_uses_generic_solver():
+    """Standardized with embedding_dim > 32 is outside the device-resident solver: the host-stepped solver
+    drives the same CUDA objective and the Gram/eigh retraction; the constraint must hold at the end."""
+    import pymde_b200 as pm
+    n, m = 600, 40
+    mde0, edges, w = _knn_problem(pm, n, 6, 2, 5, pm.Centered())
+    f = pm.penalties.Quadratic(torch.tensor(np.abs(w), device="cuda"))
+    mde = pm.MDE(n, m, torch.tensor(edges, device="cuda"), f, pm.Standardized())
+    pm.seed(0)
+    X = mde.embed(max_iter=15)
+    X64 = X.double()
+    np.testing.assert_allclose((X64.T @ X64 / n).cpu().numpy(), np.eye(m), atol=2e-4)
+    assert mde.solve_stats.average_distortions[-1] < mde.solve_stats.average_distortions[0]
+
+
+def test_verbose_and_snapshots_follow_the_reference_cadence(capsys):
+    import pymde_b200 as pm
+    mde, edges, w = _knn_problem(pm, 500, 5, 2, 6, pm.Centered())
+    pm.seed(0)
+    mde.embed(max_iter=20, snapshot_every=5, verbose=True, print_every=10)
+    st = mde.solve_stats
+    assert len(st.snapshots) == 4 and st.snapshots[0].device.type == "cpu"  # iterations 0,5,10,15 (optim.py:127-128)
+    assert st.iterations == 20 and len(st.times) == 20
