@@ -235,3 +235,25 @@ def test_verbose_and_snapshots_follow_the_reference_cadence(capsys):
     st = mde.solve_stats
     assert len(st.snapshots) == 4 and st.snapshots[0].device.type == "cpu"  # iterations 0,5,10,15 (optim.py:127-128)
     assert st.iterations == 20 and len(st.times) == 20
+
+
+@pytest.mark.parametrize("m,cname", [(20, "centered"), (8, "standardized"), (5, "centered"), (33, "centered")])
+def test_wide_embeddings_follow_the_oracle(m, cname):
+    """Group-per-edge kernel + generic projections (m >= 5; Jacobi retraction for Standardized) inside the device
+    solver, against the fp32 oracle trajectory on the same inputs."""
+    import pymde_b200 as pm
+    rng = np.random.default_rng(m)
+    n = 150
+    mde0, edges, w = _knn_problem(pm, n, 4, 2, 10 + m, pm.Centered())
+    cons, ocons = (pm.Centered(), O.Centered()) if cname == "centered" else (pm.Standardized(), O.Standardized())
+    X0 = rng.standard_normal((n, m)).astype(np.float32)
+    X0 = ocons.project(X0).astype(np.float32)
+    f = pm.penalties.PushAndPull(torch.tensor(w, device="cuda"), pm.penalties.Log1p, pm.penalties.Log)
+    mde = pm.MDE(n, m, torch.tensor(edges, device="cuda"), f, cons)
+    mde.embed(X=torch.tensor(X0, device="cuda"), max_iter=8, eps=1e-7)
+    spec = O.FnSpec(O.P_LOG1P, w, (1.5, 0, 0), fn_rep=O.P_LOG, rep=(1.0, 0, 0))
+    _, st = O.embed(X0, edges, spec, ocons, eps=1e-7, max_iter=8, dtype=np.float32)
+    k = 4
+    np.testing.assert_allclose(mde.solve_stats.average_distortions[:k], st.average_distortions[:k], rtol=2e-3)
+    np.testing.assert_allclose(mde.solve_stats.residual_norms[0], st.residual_norms[0], rtol=1e-4)
+    assert mde.solve_stats.average_distortions[-1] < mde.solve_stats.average_distortions[0]
