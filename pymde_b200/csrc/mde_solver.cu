@@ -144,7 +144,7 @@ __device__ void ls_update_body(SolverState* __restrict__ S, const double* __rest
 __device__ void fresh_finish_body(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
                                   const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
                                   double p_total);
-__device__ void iter_end_body(SolverState* __restrict__ S);
+__device__ void iter_end_body(SolverState* __restrict__ S, cudaGraphConditionalHandle h_if_next);
 
 constexpr int kScalarSmemBytes = (int)(sizeof(double) * (kMaxSlices * kDotsPerSlice + 5 * kSlots) + 64 + sizeof(LbfgsState));
 
@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kVecThreads)
 lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, const float* __restrict__ gprev,
                   const float* __restrict__ d, float* __restrict__ Sb, float* __restrict__ Yb,
                   int64_t npad, double* __restrict__ part, Tail tl) {
+  pdl_trigger();
   if (off(&S->active)) return;
   __shared__ __align__(16) unsigned char raw[sizeof(float) * kDotsPerSlice * kVecThreads];
   static_assert(sizeof(raw) >= kScalarSmemBytes, "scalar epilogue must fit in the reduction tile");
@@ -416,6 +417,7 @@ direction_apply_kernel(SolverState* __restrict__ S, const float* __restrict__ g,
                        float* __restrict__ d, const float* __restrict__ X, float* __restrict__ xinit,
                        const float* __restrict__ Sb, const float* __restrict__ Yb, int64_t npad,
                        double* __restrict__ part, int mcols, Tail tl) {
+  pdl_wait();  // dependent launch: the two-loop coefficients come from the last block of lbfgs_dots_kernel
   if (off(&S->active)) return;
   __shared__ float cs[kMaxMemory], cy[kMaxMemory];
   __shared__ const float* ps[kMaxMemory];
@@ -536,7 +538,8 @@ template <bool FINAL>
 __global__ void __launch_bounds__(kVecThreads)
 trial_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, const float* __restrict__ d,
                   float* __restrict__ X, int64_t npad, int64_t nvalid, int center_m, float* __restrict__ gz,
-                  int fuse_end) {
+                  int fuse_end, cudaGraphConditionalHandle h_if_next) {
+  if (!FINAL) pdl_trigger();  // the scatter kernel may become resident and prefetch its edge records
   if (off(&S->active)) return;
   if (!FINAL && off(&S->ls_active)) return;
   const float t = FINAL ? (float)S->ls.t_accept : (float)S->ls.t;
@@ -570,7 +573,7 @@ trial_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, 
     }
     if (!FINAL && gz != nullptr) reinterpret_cast<float4*>(gz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (FINAL && fuse_end && last_block_done(&S->tickets[3])) iter_end_body(S);
+  if (FINAL && fuse_end && last_block_done(&S->tickets[3])) iter_end_body(S, h_if_next);
 }
 
 __global__ void __launch_bounds__(kVecThreads)
@@ -608,6 +611,7 @@ pack_loss_kernel(const int* flag, const double* __restrict__ lpart, int nl, floa
 __global__ void __launch_bounds__(kVecThreads)
 grad_dots_kernel(const int* flag, const float* __restrict__ g, const float* __restrict__ d, int64_t npad,
                  double* __restrict__ part, SolverState* __restrict__ S, Tail tl) {
+  pdl_wait();  // dependent launch: the scatter kernel (or the tangent projection) must have finished
   if (off(flag)) return;
   double acc[3] = {0.0, 0.0, 0.0};
   float fa[3] = {0.0f, 0.0f, 0.0f};
@@ -713,7 +717,9 @@ ls_update_kernel(SolverState* __restrict__ S, const double* __restrict__ lpart, 
 }
 
 // S5: end of iteration (optim.py:135-173)
-__device__ void iter_end_body(SolverState* __restrict__ S) {
+// `h_if_next`: in a graph that chains several iterations, the gate of the NEXT iteration's fresh-evaluation
+// IF node is set here instead of by a separate one-thread kernel (0 = none).
+__device__ void iter_end_body(SolverState* __restrict__ S, cudaGraphConditionalHandle h_if_next) {
   if (threadIdx.x != 0) return;
   const int it = S->iter;
   const double h = S->ls.t_accept;
@@ -725,11 +731,12 @@ __device__ void iter_end_body(SolverState* __restrict__ S) {
   else if (h == 0.0) { lbfgs_reset(S->lb, S->lb.memory); S->need_fresh = 1; }  // opt.reset()
   else S->need_fresh = 0;
   if (S->iter >= S->max_stats) S->active = 0;
+  if (h_if_next) cudaGraphSetConditional(h_if_next, (S->active && S->need_fresh) ? 1u : 0u);
 }
 
-__global__ void iter_end_kernel(SolverState* __restrict__ S) {
-  if (off(&S->active)) return;
-  iter_end_body(S);
+__global__ void iter_end_kernel(SolverState* __restrict__ S, cudaGraphConditionalHandle h_if_next) {
+  if (off(&S->active)) return;  // the next IF handle keeps its default (0): nothing runs any more
+  iter_end_body(S, h_if_next);
 }
 
 __global__ void init_state_kernel(SolverState* S, double eps, int memory, int max_stats, int world,
@@ -781,8 +788,12 @@ struct mde_solver {
   // mode 1: one CUDA graph per iteration with an IF node (fresh evaluation) and a WHILE node (trials)
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
+  // the same iteration chained `unroll` times in one graph: one graph launch per `unroll` iterations
+  cudaGraph_t graph_u = nullptr;
+  cudaGraphExec_t graph_exec_u = nullptr;
+  int unroll = 1;
   cudaStream_t cap_stream = nullptr, cap_stream2 = nullptr;
-  cudaGraphConditionalHandle h_if = 0, h_while = 0;
+  cudaGraphConditionalHandle h_if = 0, h_while = 0, h_if_next = 0;  // capture-time only
   int graph_kernels_fixed = 0, graph_kernels_trial = 0, graph_kernels_fresh = 0;
 };
 
@@ -852,7 +863,8 @@ int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cud
     }
   }
   Tail tl = make_tail(s, tail_mode);
-  grad_dots_kernel<<<s->nvb, kVecThreads, 0, st>>>(flag, s->g, s->d, s->npad, s->dpart, s->S, tl);
+  MDE_CUDA_TRY(launch_dependent(grad_dots_kernel, dim3(s->nvb), dim3(kVecThreads), st, flag, (const float*)s->g,
+                                (const float*)s->d, s->npad, s->dpart, s->S, tl));
   MDE_LAUNCH_CHECK();
   return 0;
 }
@@ -878,8 +890,14 @@ int enqueue_direction(mde_solver* s, cudaStream_t st) {
     direction_scalar_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb);
     MDE_LAUNCH_CHECK();
   }
-  direction_apply_kernel<<<s->nvb, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->X, s->xinit, s->Sb,
-                                                         s->Yb, s->npad, s->dpart, s->center_m, tl);
+  if (s->fuse) {  // stream predecessor is lbfgs_dots_kernel
+    MDE_CUDA_TRY(launch_dependent(direction_apply_kernel, dim3(s->nvb), dim3(kVecThreads), st, s->S, (const float*)s->g,
+                                  s->gprev, s->d, (const float*)s->X, s->xinit, (const float*)s->Sb,
+                                  (const float*)s->Yb, s->npad, s->dpart, s->center_m, tl));
+  } else {
+    direction_apply_kernel<<<s->nvb, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->X, s->xinit, s->Sb,
+                                                           s->Yb, s->npad, s->dpart, s->center_m, tl);
+  }
   MDE_LAUNCH_CHECK();
   if (!s->fuse) {
     ls_init_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb, s->n, s->h_while);
@@ -889,7 +907,7 @@ int enqueue_direction(mde_solver* s, cudaStream_t st) {
 }
 
 int enqueue_trial(mde_solver* s, cudaStream_t st) {
-  trial_axpy_kernel<false><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, s->g, 0);
+  trial_axpy_kernel<false><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, s->g, 0, 0);
   MDE_LAUNCH_CHECK();
   int rc = enqueue_project(s, st);
   if (rc) return rc;
@@ -907,12 +925,12 @@ int enqueue_finish(mde_solver* s, cudaStream_t st) {
   // iter_end may ride in the axpy's last block only when no projection kernel follows (it can clear `active`)
   const int fuse_end = (s->fuse && s->opts.constraint == MDE_CONSTRAINT_CENTERED && s->center_m) ? 1 : 0;
   trial_axpy_kernel<true><<<s->nvb, kVecThreads, 0, st>>>(s->S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m,
-                                                          nullptr, fuse_end);
+                                                          nullptr, fuse_end, s->h_if_next);
   MDE_LAUNCH_CHECK();
   int rc = enqueue_project(s, st);
   if (rc) return rc;
   if (!fuse_end) {
-    iter_end_kernel<<<1, 32, 0, st>>>(s->S);
+    iter_end_kernel<<<1, 32, 0, st>>>(s->S, s->h_if_next);
     MDE_LAUNCH_CHECK();
   }
   return 0;
@@ -923,10 +941,10 @@ int enqueue_finish(mde_solver* s, cudaStream_t st) {
 //   -> accepted step + projection + iter_end.
 // The conditional handles are written on the device (cudaGraphSetConditional), so the host never reads
 // a scalar during an iteration.
-int build_iteration_graph(mde_solver* s) {
+int build_iteration_graph(mde_solver* s, int copies, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out) {
 #define GTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
-  GTRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
-  GTRY(cudaStreamCreateWithFlags(&s->cap_stream2, cudaStreamNonBlocking));
+  if (!s->cap_stream) GTRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+  if (!s->cap_stream2) GTRY(cudaStreamCreateWithFlags(&s->cap_stream2, cudaStreamNonBlocking));
   cudaStream_t st = s->cap_stream, st2 = s->cap_stream2;
   cudaStreamCaptureStatus cs;
   cudaGraph_t cg = nullptr;
@@ -934,13 +952,27 @@ int build_iteration_graph(mde_solver* s) {
   size_t nd = 0;
   int rc;
   const unsigned long long l0 = g_launch_count;
+  struct PdlScope {  // programmatic dependent launches only inside the captured graph
+    PdlScope() { const char* ev = getenv("MDE_B200_PDL"); g_pdl = (ev && ev[0] == '1') ? 1 : 0; }
+    ~PdlScope() { g_pdl = 0; }
+  } pdl_scope;
   GTRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  // every conditional node owns its handles (default 0 at each graph launch); the kernels enqueued
+  // below capture them by value
+  cudaGraphConditionalHandle hif[8], hwh[8];
   GTRY(cudaStreamGetCaptureInfo_v2(st, &cs, nullptr, &cg, &deps, &nd));
-  GTRY(cudaGraphConditionalHandleCreate(&s->h_if, cg, 0, cudaGraphCondAssignDefault));
-  GTRY(cudaGraphConditionalHandleCreate(&s->h_while, cg, 0, cudaGraphCondAssignDefault));
-  fresh_gate_kernel<<<1, 32, 0, st>>>(s->S, s->h_if);
-  ++g_launch_count;
-  GTRY(cudaPeekAtLastError());
+  for (int copy = 0; copy < copies; ++copy) {
+    GTRY(cudaGraphConditionalHandleCreate(&hif[copy], cg, 0, cudaGraphCondAssignDefault));
+    GTRY(cudaGraphConditionalHandleCreate(&hwh[copy], cg, 0, cudaGraphCondAssignDefault));
+  }
+  for (int copy = 0; copy < copies; ++copy) {
+  s->h_if = hif[copy]; s->h_while = hwh[copy];
+  s->h_if_next = (copy + 1 < copies) ? hif[copy + 1] : 0;
+  if (copy == 0) {  // later copies: the gate is set by the previous copy's iter_end
+    fresh_gate_kernel<<<1, 32, 0, st>>>(s->S, s->h_if);
+    ++g_launch_count;
+    GTRY(cudaPeekAtLastError());
+  }
   {  // IF node: closure() at the current iterate when lbfgs n_iter == 0
     GTRY(cudaStreamGetCaptureInfo_v2(st, &cs, nullptr, &cg, &deps, &nd));
     cudaGraphNodeParams np = {};
@@ -981,9 +1013,12 @@ int build_iteration_graph(mde_solver* s) {
     GTRY(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
   }
   if ((rc = enqueue_finish(s, st))) return rc;
-  GTRY(cudaStreamEndCapture(st, &s->graph));
-  GTRY(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
-  s->graph_kernels_fixed = (int)(g_launch_count - l0) - s->graph_kernels_trial - s->graph_kernels_fresh;
+  }  // copies
+  GTRY(cudaStreamEndCapture(st, graph_out));
+  GTRY(cudaGraphInstantiate(exec_out, *graph_out, 0));
+  s->h_if = s->h_while = s->h_if_next = 0;
+  if (copies == 1)  // kernels of one iteration outside the conditional bodies (gate included)
+    s->graph_kernels_fixed = (int)(g_launch_count - l0) - s->graph_kernels_trial - s->graph_kernels_fresh;
   g_launch_count = l0;  // capture enqueued nothing; launches are counted per graph launch
   return 0;
 #undef GTRY
@@ -1040,8 +1075,15 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   if (opts->mode == 1) {
     s->nl = 0;
     TRY(cudaStreamSynchronize(st));
-    rc = build_iteration_graph(s);
+    rc = build_iteration_graph(s, 1, &s->graph, &s->graph_exec);
     if (rc) goto fail;
+    { const char* ev = getenv("MDE_B200_UNROLL"); if (ev) s->unroll = atoi(ev); }
+    if (s->unroll < 1) s->unroll = 1;
+    if (s->unroll > 8) s->unroll = 8;
+    if (s->unroll > 1) {
+      rc = build_iteration_graph(s, s->unroll, &s->graph_u, &s->graph_exec_u);
+      if (rc) goto fail;
+    }
   }
   *out = s;
   return 0;
@@ -1059,6 +1101,8 @@ int mde_solver_destroy(mde_solver_t* s) {
   cudaFree(s->anchors); cudaFree(s->anchor_values);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   if (s->graph) cudaGraphDestroy(s->graph);
+  if (s->graph_exec_u) cudaGraphExecDestroy(s->graph_exec_u);
+  if (s->graph_u) cudaGraphDestroy(s->graph_u);
   if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
   if (s->cap_stream2) cudaStreamDestroy(s->cap_stream2);
   delete s;
@@ -1095,13 +1139,17 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
     int left = iters;
     while (left > 0 && s->host_active) {
       const int batch = left < 16 ? left : 16;
-      for (int b = 0; b < batch; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->graph_exec, st));
+      int b = 0, chained = 0;
+      for (; s->unroll > 1 && b + s->unroll <= batch; b += s->unroll, ++chained)
+        MDE_CUDA_TRY(cudaGraphLaunch(s->graph_exec_u, st));
+      for (; b < batch; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->graph_exec, st));
       left -= batch;
       if ((rc = read_status(s, st))) return rc;
       s->host_active = s->status_host[0];
       // kernels executed by the graphs: fixed part per launch + one trial body per evaluation
       g_launch_count += (unsigned long long)batch * s->graph_kernels_fixed +
                         (unsigned long long)(s->status_host[7] - s->host_evals) * s->graph_kernels_trial;
+      g_launch_count -= (unsigned long long)chained * (s->unroll - 1);  // chained copies carry no gate kernel
       s->host_evals = s->status_host[7];
       if (s->status_host[3]) { if (iters_done) *iters_done = s->status_host[2]; return s->status_host[3]; }
     }

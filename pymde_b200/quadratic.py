@@ -31,12 +31,23 @@ def spectral(n_items, embedding_dim, edges, weights, max_iter=1000, device=None,
     L = _laplacian(int(n_items), edges, weights)
     k = int(embedding_dim) + 1
     rng = np.random.default_rng(0)
+    if int(n_items) <= max(k + 1, 32):  # Lanczos needs k < n; tiny problems go through a dense eigensolver
+        vals, vecs = np.linalg.eigh(L.toarray())
+        vals, vecs = vals[:k], vecs[:, :k]
+        if vecs.shape[1] < k:  # fewer items than requested directions: pad with random columns
+            vecs = np.concatenate([vecs, rng.standard_normal((int(n_items), k - vecs.shape[1]))], 1)
+            vals = np.concatenate([vals, np.full(k - vals.shape[0], np.inf)])
+        return _finish(vals, vecs, k, n_items, device)
     try:
         vals, vecs = scipy.sparse.linalg.eigsh(L, k=k, sigma=-1e-3 * max(1.0, L.diagonal().mean()), which="LM",
                                                maxiter=max_iter, v0=rng.standard_normal(int(n_items)))
     except Exception:
         vals, vecs = scipy.sparse.linalg.eigsh(L, k=k, which="SA", maxiter=max_iter * 10,
                                                v0=rng.standard_normal(int(n_items)))
+    return _finish(vals, vecs, k, n_items, device)
+
+
+def _finish(vals, vecs, k, n_items, device):
     order = np.argsort(vals)
     X = torch.tensor(vecs[:, order[1:k]].astype(np.float32))
     if torch.cuda.is_available():

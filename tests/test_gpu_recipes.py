@@ -94,3 +94,85 @@ def test_preserve_distances_standardized_scales_deviations():
     np.testing.assert_allclose(float(d.pow(2).mean().sqrt()), nat, rtol=1e-5)
     mde.embed(max_iter=30)
     assert mde.solve_stats.average_distortions[-1] < mde.solve_stats.average_distortions[0]
+
+
+def test_knn_tiny_known_answer():
+    # pymde/test_recipes.py:12-26
+    from pymde_b200 import preprocess
+    g = preprocess.data_matrix.k_nearest_neighbors(np.array([[0.0], [1.0], [1.5], [1.75]]), k=2)
+    assert g.edges.tolist() == [[0, 1], [0, 2], [1, 2], [1, 3], [2, 3]]
+    assert g.weights.tolist() == [1.0, 1.0, 2.0, 2.0, 2.0]
+
+
+def test_standardized_initialization():
+    # pymde/test_optim.py:13-18
+    import pymde_b200 as pm
+    torch.manual_seed(0)
+    X = pm.Standardized().initialization(5, 3, device="cuda")
+    np.testing.assert_allclose((X.T @ X / 5).cpu().numpy(), np.eye(3), atol=1e-5)
+
+
+def test_docs_example_reaches_6_2884():
+    # docs_src/source/mde/index.rst:193-286: 5 items, 4 edges, Quadratic [1,2,5,6], Standardized
+    import pymde_b200 as pm
+    edges = torch.tensor([[0, 1], [0, 4], [1, 2], [2, 3]])
+    weights = torch.tensor([1.0, 2.0, 5.0, 6.0])
+    for s in range(3):
+        torch.manual_seed(s)
+        mde = pm.MDE(n_items=5, embedding_dim=2, edges=edges, distortion_function=pm.penalties.Quadratic(weights),
+                     constraint=pm.Standardized())
+        E = mde.embed()
+        np.testing.assert_allclose(mde.average_distortion(E).item(), 6.2884, rtol=2e-4)
+        np.testing.assert_allclose((E.T @ E / 5).cpu().numpy(), np.eye(2), atol=1e-4)
+        assert float(E.mean(0).abs().max()) < 1e-5
+
+
+def test_laplacian_embedding_is_quadratic_preserve_neighbors():
+    # pymde/test_recipes.py:30-51: the two constructions agree after a Procrustes alignment
+    import pymde_b200 as pm
+    torch.manual_seed(0)
+    Y = torch.randn(100, 10)
+    pm.seed(0)
+    a = pm.laplacian_embedding(Y).embed()
+    pm.seed(0)
+    b = pm.preserve_neighbors(Y, attractive_penalty=pm.penalties.Quadratic, repulsive_penalty=None).embed()
+    b = pm.util.align(source=b, target=a)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=5e-3)
+
+
+def test_anchor_initialization_and_no_anchor_anchor_edges():
+    # pymde/test_recipes.py:52-111
+    import pymde_b200 as pm
+    pm.seed(0)
+    Y = torch.randn(10, 5)
+    anchors = torch.tensor([0, 1, 3], device="cuda")
+    values = torch.tensor([2.0, 1.0, 3.0], device="cuda").reshape(3, 1)
+    c = pm.Anchored(anchors, values)
+    for init in ("random", "quadratic"):
+        mde = pm.preserve_neighbors(Y, embedding_dim=1, constraint=c, init=init)
+        np.testing.assert_allclose(mde._X_init[anchors].cpu().numpy(), values.cpu().numpy())
+    pm.seed(0)
+    Y = torch.randn(3, 2)
+    c = pm.Anchored(torch.tensor([0, 1], device="cuda"), torch.tensor([2.0, 3.0], device="cuda").reshape(2, 1))
+    mde = pm.preserve_distances(Y, embedding_dim=1, constraint=c)
+    assert mde.edges.tolist() == [[0, 2], [1, 2]]
+    mde = pm.preserve_neighbors(Y, embedding_dim=1, constraint=c)
+    assert mde.edges.tolist() == [[0, 2], [1, 2]]
+    E = mde.embed(max_iter=20)
+    np.testing.assert_allclose(E[:2].cpu().numpy(), [[2.0], [3.0]])
+
+
+@pytest.mark.parametrize("n_items", [36, 1001])
+def test_distances_reproducibility(n_items):
+    # pymde/test_recipes.py:137-159: same seed => bit-identical edges and deviations
+    import pymde_b200 as pm
+    torch.manual_seed(0)
+    Y = torch.rand((n_items, 128))
+    prev = None
+    for _ in range(3):
+        pm.seed(0)
+        mde = pm.preserve_distances(Y, max_distances=1e5)
+        cur = (mde.edges.clone(), mde.distortion_function.deviations.clone())
+        if prev is not None:
+            assert torch.equal(cur[0], prev[0]) and torch.equal(cur[1], prev[1])
+        prev = cur

@@ -74,3 +74,20 @@ def test_shard_ranges_partition_the_edge_list():
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_spectral_initialisation_is_standardized_and_spectral():
+    # pymde/quadratic.py:122-179: bottom non-trivial eigenvectors of the Laplacian, standardized
+    from pymde_b200 import quadratic
+    for n, m in ((3, 1), (10, 1), (5, 2), (40, 2), (300, 3)):
+        e = torch.tensor([[i, (i + 1) % n] for i in range(n if n > 3 else n - 1)])
+        X = quadratic.spectral(n, m, e, torch.ones(e.shape[0])).double().cpu()
+        np.testing.assert_allclose((X.T @ X / n).numpy(), np.eye(m), atol=1e-5)
+        assert float(X.mean(0).abs().max()) < 1e-5
+    # a cycle embeds as a circle: sum of squared edge lengths equals n * 2 * (1 - cos(2 pi / n)) * ... (m = 2)
+    n = 40
+    e = torch.tensor([[i, (i + 1) % n] for i in range(n)])
+    X = quadratic.spectral(n, 2, e, torch.ones(n)).double().cpu()
+    d2 = (X[e[:, 0]] - X[e[:, 1]]).pow(2).sum(1)
+    lam = 2.0 * (1.0 - np.cos(2.0 * np.pi / n))  # smallest non-zero Laplacian eigenvalue of the cycle (double)
+    np.testing.assert_allclose(float(d2.sum()), 2.0 * n * lam, rtol=1e-4)
