@@ -154,7 +154,9 @@ typedef struct mde_solver_opts {
   int32_t constraint;       /* MDE_CONSTRAINT_* */
   int32_t memory_size;      /* L-BFGS history (optim.py:110) */
   int32_t max_iter;         /* capacity of the statistics arrays */
-  int32_t mode;             /* 0 = host-stepped line search, 1 = device-driven (CUDA graph, while-node) */
+  int32_t mode;             /* 0 = host-stepped line search; 1 = CUDA graph per iteration with IF / WHILE
+                               conditional nodes; 2 = flat graph of gated "steps" (one closure evaluation each),
+                               no conditional nodes -- the fastest on B200 */
   int64_t n_anchors;        /* MDE_CONSTRAINT_ANCHORED */
   const int64_t* anchors;   /* device (n_anchors,) */
   const float* anchor_values; /* device (n_anchors, m) */

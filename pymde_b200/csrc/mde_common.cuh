@@ -29,25 +29,6 @@ extern unsigned long long g_launch_count;  // host-side counter (mde_launch_coun
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
-// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may become resident while its
-// stream predecessor is still running; it must execute pdl_wait() before touching anything the predecessor
-// writes (flags included).  Without the attribute both instructions are no-ops.  g_pdl is switched on by the
-// solver while it captures its iteration graph (MDE_B200_PDL=1).
-extern int g_pdl;
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr unsigned kFull = 0xffffffffu;
 

@@ -28,7 +28,6 @@
 
 namespace mde {
 unsigned long long g_launch_count = 0;
-int g_pdl = 0;
 }
 
 using namespace mde;
@@ -234,6 +233,7 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
                        int64_t p, const float* __restrict__ X, float* __restrict__ grad,
                        double* __restrict__ loss_partials, FnDev fn, float inv_p,
                        const int* __restrict__ flag) {
+  if (flag != nullptr && *flag == 0) return;
   constexpr int E = 4 * NQ;  // consecutive edges owned by a thread per iteration
   const int64_t nquads = (p + 3) >> 2;
   const int64_t nunits = (nquads + NQ - 1) / NQ;
@@ -253,11 +253,6 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
       a4n = __ldg(reinterpret_cast<const float4*>(par0) + u0);
     }
   }
-  // The edge records are immutable, so the prefetch above may run while the stream predecessor (the trial
-  // axpy) is still writing X; everything below reads what it wrote.
-  pdl_trigger();
-  pdl_wait();
-  if (flag != nullptr && *flag == 0) return;
   for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nunits; u += stride) {
     int s[E], t[E];
     float a[E], b[E];
@@ -592,7 +587,7 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
       e->loss_partials, e->fn, inv_p, flag)
   // hot function combinations get compile-time ids (fused mode, m = 2 / 3); the rest use the table
 #define QUADK_(MM, FA, FR, FAST, NQV)                                                                 \
-  launch_dependent(distortion_quad_kernel<MM, MODE, FA, FR, FAST, NQV>, dim3(nb), dim3(kQuadThreads), st, \
+  distortion_quad_kernel<MM, MODE, FA, FR, FAST, NQV><<<nb, kQuadThreads, 0, st>>>(                   \
       e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
       e->loss_partials, e->fn, inv_p, flag)
 #define QUADK(MM, FA, FR, FAST)                                                                       \

@@ -46,9 +46,11 @@ constexpr int kVecBlocks = kNumSMs * 2;
 constexpr int kPairsPerSlice = 8;
 constexpr int kDotsPerSlice = 4 + 5 * kPairsPerSlice;  // 44
 constexpr int kMaxSlices = kMaxMemory / kPairsPerSlice;  // 4
+constexpr int kStatusInts = 12;
+enum { PH_DIR = 0, PH_TRIAL = 1, PH_FRESH = 2, PH_MAT = 3 };  // mode 2: phase of a step
 
 struct SolverState {
-  // ---- status word (first 32 bytes, copied to the host) ----
+  // ---- status word (first kStatusInts ints, copied to the host) ----
   int active;      // kernels exit early when 0
   int converged;   // residual test fired (optim.py:165)
   int iter;        // completed iterations
@@ -56,7 +58,16 @@ struct SolverState {
   int need_fresh;  // lbfgs n_iter == 0: evaluate at X before the direction update
   int ls_active;   // line search wants another trial
   int stop_after;  // residual <= eps seen at the start of this iteration
-  int pad0;
+  int pad0;        // low word of func_evals
+  // ---- mode 2 (flat step graph) ----
+  int paused;      // stopped at iter_limit; mde_solver_run resumes it
+  int phase;       // what the next step does (PH_*)
+  int iter_limit;  // pause when `iter` reaches it
+  int pad1;
+  int g_dir;       // gates of the next step, written by the step epilogue: direction kernels run
+  int g_eval;      //   closure evaluation (scatter kernel, tangent projection, dots) runs
+  int g_mat;       //   the axpy materialises the ACCEPTED point (no evaluation follows)
+  int g_proj;      //   the iterate moved: retraction kernels run
   // ---- scalars ----
   double eps;
   double loss;     // f at the current iterate (cached loss, lbfgs.py:418-426,550)
@@ -145,6 +156,9 @@ __device__ void fresh_finish_body(SolverState* __restrict__ S, const double* __r
                                   const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
                                   double p_total);
 __device__ void iter_end_body(SolverState* __restrict__ S, cudaGraphConditionalHandle h_if_next);
+__device__ void step_end_body(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
+                              const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
+                              double p_total);
 
 constexpr int kScalarSmemBytes = (int)(sizeof(double) * (kMaxSlices * kDotsPerSlice + 5 * kSlots) + 64 + sizeof(LbfgsState));
 
@@ -154,9 +168,9 @@ constexpr int kScalarSmemBytes = (int)(sizeof(double) * (kMaxSlices * kDotsPerSl
 __global__ void __launch_bounds__(kVecThreads)
 lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, const float* __restrict__ gprev,
                   const float* __restrict__ d, float* __restrict__ Sb, float* __restrict__ Yb,
-                  int64_t npad, double* __restrict__ part, Tail tl) {
-  pdl_trigger();
+                  int64_t npad, double* __restrict__ part, Tail tl, const int* __restrict__ gate) {
   if (off(&S->active)) return;
+  if (gate != nullptr && off(gate)) return;
   __shared__ __align__(16) unsigned char raw[sizeof(float) * kDotsPerSlice * kVecThreads];
   static_assert(sizeof(raw) >= kScalarSmemBytes, "scalar epilogue must fit in the reduction tile");
   const int slice = blockIdx.y;
@@ -416,9 +430,9 @@ __global__ void __launch_bounds__(kVecThreads)
 direction_apply_kernel(SolverState* __restrict__ S, const float* __restrict__ g, float* __restrict__ gprev,
                        float* __restrict__ d, const float* __restrict__ X, float* __restrict__ xinit,
                        const float* __restrict__ Sb, const float* __restrict__ Yb, int64_t npad,
-                       double* __restrict__ part, int mcols, Tail tl) {
-  pdl_wait();  // dependent launch: the two-loop coefficients come from the last block of lbfgs_dots_kernel
+                       double* __restrict__ part, int mcols, Tail tl, const int* __restrict__ gate) {
   if (off(&S->active)) return;
+  if (gate != nullptr && off(gate)) return;
   __shared__ float cs[kMaxMemory], cy[kMaxMemory];
   __shared__ const float* ps[kMaxMemory];
   __shared__ const float* py[kMaxMemory];
@@ -539,7 +553,6 @@ __global__ void __launch_bounds__(kVecThreads)
 trial_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, const float* __restrict__ d,
                   float* __restrict__ X, int64_t npad, int64_t nvalid, int center_m, float* __restrict__ gz,
                   int fuse_end, cudaGraphConditionalHandle h_if_next) {
-  if (!FINAL) pdl_trigger();  // the scatter kernel may become resident and prefetch its edge records
   if (off(&S->active)) return;
   if (!FINAL && off(&S->ls_active)) return;
   const float t = FINAL ? (float)S->ls.t_accept : (float)S->ls.t;
@@ -611,7 +624,13 @@ pack_loss_kernel(const int* flag, const double* __restrict__ lpart, int nl, floa
 __global__ void __launch_bounds__(kVecThreads)
 grad_dots_kernel(const int* flag, const float* __restrict__ g, const float* __restrict__ d, int64_t npad,
                  double* __restrict__ part, SolverState* __restrict__ S, Tail tl) {
-  pdl_wait();  // dependent launch: the scatter kernel (or the tangent projection) must have finished
+  if (tl.mode == 3) {  // mode 2 step: `flag` is the evaluation gate; PH_MAT has no evaluation, only the epilogue
+    if (off(&S->active)) return;
+    if (S->g_mat) {  // the epilogue rewrites the gates: run it once every block has read them
+      if (last_block_done(&S->tickets[2])) step_end_body(S, tl.lpart, tl.nl, tl.tail, part, gridDim.x, tl.p_total);
+      return;
+    }
+  }
   if (off(flag)) return;
   double acc[3] = {0.0, 0.0, 0.0};
   float fa[3] = {0.0f, 0.0f, 0.0f};
@@ -638,6 +657,7 @@ grad_dots_kernel(const int* flag, const float* __restrict__ g, const float* __re
   }
   if (tl.fuse && last_block_done(&S->tickets[2])) {
     if (tl.mode == 1) ls_update_body(S, tl.lpart, tl.nl, tl.tail, part, gridDim.x, tl.p_total, tl.h_while);
+    else if (tl.mode == 3) step_end_body(S, tl.lpart, tl.nl, tl.tail, part, gridDim.x, tl.p_total);
     else fresh_finish_body(S, tl.lpart, tl.nl, tl.tail, part, gridDim.x, tl.p_total);
   }
 }
@@ -739,6 +759,103 @@ __global__ void iter_end_kernel(SolverState* __restrict__ S, cudaGraphConditiona
   iter_end_body(S, h_if_next);
 }
 
+// ---------------------------------------------------------------------------------------
+// mode 2: the solve as a flat chain of identical "steps" (no conditional graph nodes: on B200 an IF node
+// costs ~10 us and a one-trip WHILE node ~16 us, a dependent kernel node 1.4 us --
+// profiles/r01_graph_overheads.txt).  A step = direction kernels (gated) -> axpy -> retraction (gated)
+// -> scatter kernel -> tangent projection -> dots + epilogue; it performs exactly one closure evaluation.
+// The epilogue (last block of the dots kernel) advances a small phase machine and writes the gates the
+// next step's kernels read:
+//   PH_FRESH  closure at the current iterate (lbfgs n_iter == 0)           -> PH_DIR
+//   PH_DIR    new direction + first line-search trial                      -> PH_TRIAL | PH_MAT | end of iteration
+//   PH_TRIAL  another trial of the same line search                        -> PH_TRIAL | PH_MAT | end of iteration
+//   PH_MAT    X = retract(x_init + t_accept d) when the accepted step is not the last one evaluated
+//             (otherwise X already holds it bit for bit); no evaluation     -> end of iteration
+// End of iteration (iter_end_body) -> PH_DIR, or PH_FRESH after a reset, or pause at iter_limit.
+// ---------------------------------------------------------------------------------------
+__device__ void set_phase(SolverState* __restrict__ S, int ph) {
+  S->phase = ph;
+  S->need_fresh = (ph == PH_FRESH) ? 1 : 0;
+  const int on = S->active;
+  S->g_dir = (on && ph == PH_DIR) ? 1 : 0;
+  S->g_eval = (on && ph != PH_MAT) ? 1 : 0;
+  S->g_mat = (on && ph == PH_MAT) ? 1 : 0;
+  S->g_proj = (on && ph != PH_FRESH) ? 1 : 0;
+}
+
+__device__ void step_end_body(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
+                              const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
+                              double p_total) {
+  const int ph = S->phase;  // uniform over the block
+  if (ph == PH_FRESH) fresh_finish_body(S, lpart, nl, tail, dpart, nd, p_total);
+  else if (ph != PH_MAT) ls_update_body(S, lpart, nl, tail, dpart, nd, p_total, 0);
+  if (threadIdx.x != 0) return;
+  int next = ph;
+  bool end_of_iteration = false;
+  if (ph == PH_FRESH) next = PH_DIR;
+  else if (ph == PH_MAT) end_of_iteration = true;
+  else if (S->ls_active) next = PH_TRIAL;
+  else if (S->active) {  // line search finished (on SolverError `active` is already 0)
+    if (S->ls.t_accept == S->t_eval) end_of_iteration = true;
+    else next = PH_MAT;
+  }
+  if (end_of_iteration) {
+    iter_end_body(S, 0);
+    next = S->need_fresh ? PH_FRESH : PH_DIR;
+    if (S->active && S->iter >= S->iter_limit) { S->active = 0; S->paused = 1; }
+  }
+  set_phase(S, next);
+}
+
+// mode 2: (re)arm the solver for iterations up to `limit`
+__global__ void resume_kernel(SolverState* __restrict__ S, int limit) {
+  if (threadIdx.x != 0) return;
+  S->iter_limit = limit;
+  if (S->paused && S->iter < limit) { S->paused = 0; S->active = 1; }
+  else if (S->active && S->iter >= limit) { S->active = 0; S->paused = 1; }
+  set_phase(S, S->phase);
+}
+
+// mode 2: the axpy of a step.  PH_DIR / PH_TRIAL: trial point x_init + t d (and g = 0 for the scatter that
+// follows); PH_MAT: accepted point x_init + t_accept d; PH_FRESH: only g = 0.  Centered with m in {1,2,4}
+// is applied on the fly like trial_axpy_kernel.
+__global__ void __launch_bounds__(kVecThreads)
+step_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, const float* __restrict__ d,
+                 float* __restrict__ X, int64_t npad, int64_t nvalid, int center_m, float* __restrict__ gz) {
+  if (off(&S->active)) return;
+  const bool mat = S->g_mat != 0;
+  const bool move = S->g_proj != 0;  // every phase but PH_FRESH
+  if (move && !mat && off(&S->ls_active)) return;
+  const float t = mat ? (float)S->ls.t_accept : (float)S->ls.t;
+  float mu[4] = {0.f, 0.f, 0.f, 0.f};
+  if (center_m == 1) { float v = S->mu_x[0] + t * S->mu_d[0]; mu[0] = mu[1] = mu[2] = mu[3] = v; }
+  else if (center_m == 2) {
+    float v0 = S->mu_x[0] + t * S->mu_d[0], v1 = S->mu_x[1] + t * S->mu_d[1];
+    mu[0] = mu[2] = v0; mu[1] = mu[3] = v1;
+  } else if (center_m == 4) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mu[c] = S->mu_x[c] + t * S->mu_d[c];
+  }
+  const int64_t n4 = npad >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + 1; i += stride) {
+    if (move && i < n4) {
+      float4 A = reinterpret_cast<const float4*>(xinit)[i];
+      float4 D = reinterpret_cast<const float4*>(d)[i];
+      float4 R = make_float4(fmaf(t, D.x, A.x) - mu[0], fmaf(t, D.y, A.y) - mu[1], fmaf(t, D.z, A.z) - mu[2],
+                             fmaf(t, D.w, A.w) - mu[3]);
+      if (center_m != 0 && 4 * i + 3 >= nvalid) {  // keep the zero padding behind the last row
+        if (4 * i + 0 >= nvalid) R.x = 0.f;
+        if (4 * i + 1 >= nvalid) R.y = 0.f;
+        if (4 * i + 2 >= nvalid) R.z = 0.f;
+        if (4 * i + 3 >= nvalid) R.w = 0.f;
+      }
+      reinterpret_cast<float4*>(X)[i] = R;
+    }
+    if (!mat) reinterpret_cast<float4*>(gz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 __global__ void init_state_kernel(SolverState* S, double eps, int memory, int max_stats, int world,
                                   double* avg, double* resid, double* pct, double* steplen) {
   if (threadIdx.x != 0) return;
@@ -746,6 +863,8 @@ __global__ void init_state_kernel(SolverState* S, double eps, int memory, int ma
   S->stop_after = 0; S->pad0 = 0; S->eps = eps; S->loss = 0.0; S->gg = 0.0; S->g1 = 0.0; S->gtd = 0.0f;
   S->dmax = 0.0f; S->dd = 0.0; S->xx = 0.0; S->t_last = 0.0; S->t_eval = 0.0; S->func_evals = 0;
   S->max_stats = max_stats; S->world = world;
+  S->paused = 0; S->iter_limit = max_stats; S->pad1 = 0;
+  set_phase(S, PH_FRESH);  // mode 2 (sets need_fresh = 1 as well)
   for (int k = 0; k < 4; ++k) S->tickets[k] = 0u;
   S->avg = avg; S->resid = resid; S->pct = pct; S->steplen = steplen;
   lbfgs_reset(S->lb, memory);
@@ -768,7 +887,7 @@ struct mde_solver {
   int m = 0;
   mde_solver_opts_t opts{};
   SolverState* S = nullptr;          // device
-  int* status_host = nullptr;        // pinned, 8 ints
+  int* status_host = nullptr;        // pinned, kStatusInts ints
   float *X = nullptr, *xinit = nullptr, *d = nullptr, *g = nullptr, *gprev = nullptr, *Sb = nullptr, *Yb = nullptr;
   double *dpart = nullptr;           // dot partials
   double *stats = nullptr;           // 4 * max_iter doubles
@@ -792,6 +911,11 @@ struct mde_solver {
   cudaGraph_t graph_u = nullptr;
   cudaGraphExec_t graph_exec_u = nullptr;
   int unroll = 1;
+  // mode 2: flat step graphs (one step / kStepsPerGraph steps), no conditional nodes
+  cudaGraph_t step_graph = nullptr, steps_graph = nullptr;
+  cudaGraphExec_t step_exec = nullptr, steps_exec = nullptr;
+  int step_kernels = 0;              // kernel nodes per step
+  int host_iter = 0;                 // iterations completed (last status read)
   cudaStream_t cap_stream = nullptr, cap_stream2 = nullptr;
   cudaGraphConditionalHandle h_if = 0, h_while = 0, h_if_next = 0;  // capture-time only
   int graph_kernels_fixed = 0, graph_kernels_trial = 0, graph_kernels_fresh = 0;
@@ -800,7 +924,7 @@ struct mde_solver {
 namespace {
 
 int read_status(mde_solver* s, cudaStream_t st) {
-  MDE_CUDA_TRY(cudaMemcpyAsync(s->status_host, s->S, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  MDE_CUDA_TRY(cudaMemcpyAsync(s->status_host, s->S, kStatusInts * sizeof(int), cudaMemcpyDeviceToHost, st));
   MDE_CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
@@ -863,8 +987,7 @@ int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cud
     }
   }
   Tail tl = make_tail(s, tail_mode);
-  MDE_CUDA_TRY(launch_dependent(grad_dots_kernel, dim3(s->nvb), dim3(kVecThreads), st, flag, (const float*)s->g,
-                                (const float*)s->d, s->npad, s->dpart, s->S, tl));
+  grad_dots_kernel<<<s->nvb, kVecThreads, 0, st>>>(flag, s->g, s->d, s->npad, s->dpart, s->S, tl);
   MDE_LAUNCH_CHECK();
   return 0;
 }
@@ -880,24 +1003,19 @@ int enqueue_fresh(mde_solver* s, cudaStream_t st) {
   return 0;
 }
 
-int enqueue_direction(mde_solver* s, cudaStream_t st) {
+int enqueue_direction(mde_solver* s, cudaStream_t st, const int* gate = nullptr) {
   int slices = (s->opts.memory_size + kPairsPerSlice - 1) / kPairsPerSlice;
   dim3 grid(s->nvb, slices);
   Tail tl = make_tail(s, 0);
-  lbfgs_dots_kernel<<<grid, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->Sb, s->Yb, s->npad, s->dpart, tl);
+  lbfgs_dots_kernel<<<grid, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->Sb, s->Yb, s->npad, s->dpart, tl,
+                                                  gate);
   MDE_LAUNCH_CHECK();
   if (!s->fuse) {
     direction_scalar_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb);
     MDE_LAUNCH_CHECK();
   }
-  if (s->fuse) {  // stream predecessor is lbfgs_dots_kernel
-    MDE_CUDA_TRY(launch_dependent(direction_apply_kernel, dim3(s->nvb), dim3(kVecThreads), st, s->S, (const float*)s->g,
-                                  s->gprev, s->d, (const float*)s->X, s->xinit, (const float*)s->Sb,
-                                  (const float*)s->Yb, s->npad, s->dpart, s->center_m, tl));
-  } else {
-    direction_apply_kernel<<<s->nvb, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->X, s->xinit, s->Sb,
-                                                           s->Yb, s->npad, s->dpart, s->center_m, tl);
-  }
+  direction_apply_kernel<<<s->nvb, kVecThreads, 0, st>>>(s->S, s->g, s->gprev, s->d, s->X, s->xinit, s->Sb,
+                                                         s->Yb, s->npad, s->dpart, s->center_m, tl, gate);
   MDE_LAUNCH_CHECK();
   if (!s->fuse) {
     ls_init_kernel<<<1, 256, 0, st>>>(s->S, s->dpart, s->nvb, s->n, s->h_while);
@@ -936,6 +1054,53 @@ int enqueue_finish(mde_solver* s, cudaStream_t st) {
   return 0;
 }
 
+// mode 2: one step (see step_end_body).  Every kernel is gated on the device; the chain has no host decision.
+int enqueue_step(mde_solver* s, cudaStream_t st) {
+  SolverState* S = s->S;
+  int rc = enqueue_direction(s, st, &S->g_dir);
+  if (rc) return rc;
+  step_axpy_kernel<<<s->nvb, kVecThreads, 0, st>>>(S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, s->g);
+  MDE_LAUNCH_CHECK();
+  switch (s->opts.constraint) {  // retraction of the moved iterate (project_callback, lbfgs.py:368-372)
+    case MDE_CONSTRAINT_CENTERED:
+      if (!s->center_m && (rc = enqueue_project_centered(s->X, s->n, s->m, s->pw, &S->g_proj, st))) return rc;
+      break;
+    case MDE_CONSTRAINT_STANDARDIZED:
+      if ((rc = enqueue_project_standardized(s->X, s->n, s->m, s->pw, &S->g_proj, st))) return rc;
+      break;
+    case MDE_CONSTRAINT_ANCHORED: {
+      const int64_t tot = s->opts.n_anchors * s->m;
+      if (tot > 0) {
+        anchor_rows_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(&S->g_proj, s->X, s->anchors, s->anchor_values,
+                                                                    s->opts.n_anchors, s->m);
+        MDE_LAUNCH_CHECK();
+      }
+      break;
+    }
+    default: return MDE_E_INVALID;
+  }
+  return enqueue_eval(s, &S->g_eval, false, 3, st);
+}
+
+int build_step_graph(mde_solver* s, int steps, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out) {
+#define GTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
+  if (!s->cap_stream) GTRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+  const unsigned long long l0 = g_launch_count;
+  GTRY(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeRelaxed));
+  int rc = 0;
+  for (int k = 0; k < steps && !rc; ++k) rc = enqueue_step(s, s->cap_stream);
+  cudaError_t e = cudaStreamEndCapture(s->cap_stream, graph_out);
+  if (rc) return rc;
+  GTRY(e);
+  GTRY(cudaGraphInstantiate(exec_out, *graph_out, 0));
+  s->step_kernels = (int)(g_launch_count - l0) / steps;
+  g_launch_count = l0;  // capture enqueued nothing; launches are counted per graph launch
+  return 0;
+#undef GTRY
+}
+
+constexpr int kStepsPerGraph = 8;
+
 // One iteration as a CUDA graph:
 //   fresh_gate -> IF(need_fresh){ evaluate at X } -> direction (P1,S1,P2,S2) -> WHILE(ls_active){ trial }
 //   -> accepted step + projection + iter_end.
@@ -952,10 +1117,6 @@ int build_iteration_graph(mde_solver* s, int copies, cudaGraph_t* graph_out, cud
   size_t nd = 0;
   int rc;
   const unsigned long long l0 = g_launch_count;
-  struct PdlScope {  // programmatic dependent launches only inside the captured graph
-    PdlScope() { const char* ev = getenv("MDE_B200_PDL"); g_pdl = (ev && ev[0] == '1') ? 1 : 0; }
-    ~PdlScope() { g_pdl = 0; }
-  } pdl_scope;
   GTRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
   // every conditional node owns its handles (default 0 at each graph launch); the kernels enqueued
   // below capture them by value
@@ -1035,8 +1196,8 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   if (opts->constraint == MDE_CONSTRAINT_STANDARDIZED && m > kProjMaxM) return MDE_E_UNSUPPORTED;
   if (opts->constraint < 0 || opts->constraint > MDE_CONSTRAINT_ANCHORED) return MDE_E_INVALID;
   if (opts->max_iter < 1) return MDE_E_INVALID;
-  if (opts->mode != 0 && opts->mode != 1) return MDE_E_INVALID;
-  if (opts->mode == 1 && opts->world_size > 1) return MDE_E_UNSUPPORTED;  // NCCL hook is host-stepped
+  if (opts->mode < 0 || opts->mode > 2) return MDE_E_INVALID;
+  if (opts->mode != 0 && opts->world_size > 1) return MDE_E_UNSUPPORTED;  // NCCL hook is host-stepped
   if (n != edges_n(e)) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   mde_solver* s = new (std::nothrow) mde_solver();
@@ -1047,7 +1208,7 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   int rc = 0;
 #define TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
   TRY(cudaMalloc(&s->S, sizeof(SolverState)));
-  TRY(cudaMallocHost(&s->status_host, 8 * sizeof(int)));
+  TRY(cudaMallocHost(&s->status_host, kStatusInts * sizeof(int)));
   TRY(cudaMalloc(&s->X, vb)); TRY(cudaMalloc(&s->xinit, vb)); TRY(cudaMalloc(&s->d, vb));
   TRY(cudaMalloc(&s->g, vb)); TRY(cudaMalloc(&s->gprev, vb));
   TRY(cudaMalloc(&s->Sb, (int64_t)(opts->memory_size + 1) * s->npad * sizeof(float)));
@@ -1072,6 +1233,15 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   s->nvb = vec_blocks(s->npad >> 2);
   if (opts->constraint == MDE_CONSTRAINT_CENTERED && (m == 1 || m == 2 || m == 4)) s->center_m = m;
   { const char* ev = getenv("MDE_B200_FUSE"); if (ev && ev[0] == '0') s->fuse = 0; }
+  if (opts->mode == 2) {
+    s->fuse = 1;  // the phase machine lives in the fused epilogues
+    s->nl = 0;
+    TRY(cudaStreamSynchronize(st));
+    rc = build_step_graph(s, 1, &s->step_graph, &s->step_exec);
+    if (rc) goto fail;
+    rc = build_step_graph(s, kStepsPerGraph, &s->steps_graph, &s->steps_exec);
+    if (rc) goto fail;
+  }
   if (opts->mode == 1) {
     s->nl = 0;
     TRY(cudaStreamSynchronize(st));
@@ -1101,6 +1271,10 @@ int mde_solver_destroy(mde_solver_t* s) {
   cudaFree(s->anchors); cudaFree(s->anchor_values);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   if (s->graph) cudaGraphDestroy(s->graph);
+  if (s->step_exec) cudaGraphExecDestroy(s->step_exec);
+  if (s->step_graph) cudaGraphDestroy(s->step_graph);
+  if (s->steps_exec) cudaGraphExecDestroy(s->steps_exec);
+  if (s->steps_graph) cudaGraphDestroy(s->steps_graph);
   if (s->graph_exec_u) cudaGraphExecDestroy(s->graph_exec_u);
   if (s->graph_u) cudaGraphDestroy(s->graph_u);
   if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
@@ -1126,6 +1300,7 @@ int mde_solver_begin(mde_solver_t* s, const float* X0, double eps, void* stream)
   s->host_need_fresh = 1;
   s->host_active = 1;
   s->host_evals = 0;
+  s->host_iter = 0;
   return 0;
 }
 
@@ -1133,6 +1308,48 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
   if (!s) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = 0;
+  if (s->opts.mode == 2) {
+    // flat step graphs: the device pauses itself at `target`; the host only keeps the queue fed.  A step is
+    // one closure evaluation, an iteration takes >= 1 of them, so launching `remaining` steps never overshoots
+    // by more than the gated (early-exit) kernels of the surplus steps.
+    if (!s->host_active || iters <= 0) {
+      if ((rc = read_status(s, st))) return rc;
+      if (iters_done) *iters_done = s->status_host[2];
+      if (converged) *converged = s->status_host[1];
+      return 0;
+    }
+    int target = s->host_iter + iters;
+    if (target > s->opts.max_iter) target = s->opts.max_iter;
+    resume_kernel<<<1, 32, 0, st>>>(s->S, target);
+    MDE_LAUNCH_CHECK();
+    for (int round = 0;; ++round) {
+      if (round > (1 << 20)) return MDE_E_INVALID;
+      int remaining = target - s->host_iter;
+      if (remaining < 1) remaining = 1;
+      long long steps = 0;
+      if (remaining >= kStepsPerGraph) {
+        int graphs = (remaining + remaining / 8) / kStepsPerGraph;
+        if (graphs > 8) graphs = 8;
+        for (int b = 0; b < graphs; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->steps_exec, st));
+        steps = (long long)graphs * kStepsPerGraph;
+      } else {
+        const int singles = remaining + remaining / 4 + (round > 0 ? 1 : 0);
+        for (int b = 0; b < singles; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->step_exec, st));
+        steps = singles;
+      }
+      g_launch_count += (unsigned long long)steps * s->step_kernels;
+      if ((rc = read_status(s, st))) return rc;
+      s->host_iter = s->status_host[2];
+      if (s->status_host[3]) { s->host_active = 0; if (iters_done) *iters_done = s->status_host[2]; return s->status_host[3]; }
+      if (!s->status_host[0]) {              // paused at the target, converged, or out of iterations
+        s->host_active = s->status_host[8];  // only a pause can be resumed
+        break;
+      }
+    }
+    if (iters_done) *iters_done = s->status_host[2];
+    if (converged) *converged = s->status_host[1];
+    return 0;
+  }
   if (s->opts.mode == 1) {
     // device-driven: one graph launch per iteration, status read back once per batch.  Launches
     // after convergence are no-ops (every kernel checks the device-side `active` flag).

@@ -28,9 +28,9 @@ def build(pm, key, g):
     return pm.MDE(n, m, torch.tensor(g[key + "/edges"], device="cuda"), f(), c), X0
 
 
-@pytest.fixture(params=[1, 0], ids=["graph", "hoststep"])
+@pytest.fixture(params=[2, 1, 0], ids=["steps", "graph", "hoststep"])
 def solver_mode(request):
-    """Run with the device-driven CUDA-graph solver (1) and the host-stepped one (0)."""
+    """Run with the flat step-graph solver (2), the conditional-node graph (1) and the host-stepped one (0)."""
     from pymde_b200 import optim
     old = optim.DEFAULT_MODE
     optim.DEFAULT_MODE = request.param
@@ -105,15 +105,16 @@ def test_graph_and_hoststep_modes_agree_bitwise():
     res = []
     old = optim.DEFAULT_MODE
     try:
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             optim.DEFAULT_MODE = mode
             mde, X0 = build(pm, "docs5", g)
             mde.embed(X=X0, max_iter=30, eps=1e-7)
             res.append((mde.solve_stats.iterations, list(mde.solve_stats.average_distortions)))
     finally:
         optim.DEFAULT_MODE = old
-    assert res[0][0] == res[1][0]
+    assert res[0][0] == res[1][0] == res[2][0]
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-6)
+    np.testing.assert_allclose(res[0][1], res[2][1], rtol=1e-6)
 
 
 @pytest.mark.parametrize("cname", ["centered", "standardized"])

@@ -14,8 +14,11 @@ ITERS = int(os.environ.get("VARIANT_ITERS", "400"))
 
 
 def run(cons, env):
-    for k in ("MDE_B200_UNROLL", "MDE_B200_PDL"):
+    from pymde_b200 import optim
+    for k in ("MDE_B200_UNROLL",):
         os.environ.pop(k, None)
+    env = dict(env)
+    optim.DEFAULT_MODE = int(env.pop("MODE", "1"))
     os.environ.update(env)
     f = pm.penalties.PushAndPull(wt, pm.penalties.Log1p, pm.penalties.Log)
     mde = pm.MDE(bench.N_ITEMS, 2, et, f, cons, device=dev)
@@ -27,18 +30,15 @@ def run(cons, env):
         t0 = time.perf_counter(); done, _ = solver.run(ITERS); torch.cuda.synchronize(); dt = time.perf_counter() - t0
         best = max(best, (done - 16) / dt)
     avg, res, pct, stp, fe = solver.stats(done)
-    return best, fe / done, avg[0], avg[-1]
+    return best, fe / done, avg[0], avg[-1], done
 
 
-if len(sys.argv) > 1 and sys.argv[1] == "pdl":   # separate process: a rejected capture may poison the context
-    VARIANTS = [{}, {"MDE_B200_PDL": "1"}, {"MDE_B200_PDL": "1", "MDE_B200_UNROLL": "4"}, {}]
-else:
-    VARIANTS = [{}, {"MDE_B200_UNROLL": "2"}, {"MDE_B200_UNROLL": "4"}, {"MDE_B200_UNROLL": "8"}, {}]
+VARIANTS = [{}, {"MDE_B200_UNROLL": "4"}, {"MODE": "2"}, {"MDE_B200_UNROLL": "4"}, {"MODE": "2"}]
 for cname, cons in (("centered", pm.Centered()), ("standardized", pm.Standardized())):
     for env in VARIANTS:
-        tag = " ".join("%s=%s" % (k[9:], v) for k, v in sorted(env.items())) or "default"
+        tag = " ".join("%s=%s" % (k.replace("MDE_B200_", ""), v) for k, v in sorted(env.items())) or "mode1"
         try:
             r = run(cons, env)
-            print("%-13s %-18s %8.0f it/s  evals/iter %.2f  loss %.6f -> %.6f" % ((cname, tag) + r), flush=True)
-        except Exception as ex:  # a variant the driver rejects (e.g. programmatic edges in a conditional body)
-            print("%-13s %-18s FAILED: %s" % (cname, tag, ex), flush=True)
+            print("%-13s %-12s %8.0f it/s  evals/iter %.2f  loss %.6f -> %.6f  (%d iterations)" % ((cname, tag) + r), flush=True)
+        except Exception as ex:
+            print("%-13s %-12s FAILED: %s" % (cname, tag, ex), flush=True)
