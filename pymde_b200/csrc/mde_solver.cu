@@ -90,9 +90,10 @@ struct SolverState {
 __device__ __forceinline__ bool off(const int* flag) { return *flag == 0; }
 
 // Fixed-order reduction of K sums over nb block partials into smem out[K]; all threads of the block call.
-// Thread t owns (k = t % K, segment = t / K) and walks blocks segment, segment + S, ... with independent,
-// coalesced loads (through L2: the partials may come from other SMs of the same launch); the S segment
-// sums of each k are then combined in a fixed order.  Deterministic for a given launch shape.
+// Stage 1: thread t owns (k = t % K, segment = t / K) and walks blocks segment, segment + S, ... in batches of
+// 16 independent coalesced loads (through L2: the partials may come from other SMs of the same launch).
+// Stage 2: one warp per output combines the S segment sums with a fixed shuffle tree.  The summation order
+// depends only on (nb, K, blockDim), so scalars are bit-reproducible for a given launch shape.
 template <bool MAXLAST>
 __device__ void reduce_partials(const double* __restrict__ part, int nb, int K, double* out) {
   __shared__ double red_buf[256];
@@ -101,17 +102,29 @@ __device__ void reduce_partials(const double* __restrict__ part, int nb, int K, 
   const int k = threadIdx.x % K, seg = threadIdx.x / K;
   const bool is_max = MAXLAST && (k == K - 1);
   if (threadIdx.x < S * K) {
+    constexpr int U = 16;
     double s = 0.0;
-    if (is_max) { for (int b = seg; b < nb; b += S) s = fmax(s, __ldcg(part + (int64_t)b * K + k)); }
-    else { for (int b = seg; b < nb; b += S) s += __ldcg(part + (int64_t)b * K + k); }
+    for (int b0 = seg; b0 < nb; b0 += U * S) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int b = b0 + u * S;
+        v[u] = (b < nb) ? __ldcg(part + (int64_t)b * K + k) : 0.0;  // 0 is neutral for the sums and for max |.|
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) s = is_max ? fmax(s, v[u]) : s + v[u];
+    }
     red_buf[seg * K + k] = s;
   }
   __syncthreads();
-  if (threadIdx.x < K) {
-    const bool mx = MAXLAST && (threadIdx.x == K - 1);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+  for (int kk = w; kk < K; kk += nw) {  // warp-uniform trip count
+    const bool mx = MAXLAST && (kk == K - 1);
     double s = 0.0;
-    for (int q = 0; q < S; ++q) { const double v = red_buf[q * K + threadIdx.x]; s = mx ? fmax(s, v) : s + v; }
-    out[threadIdx.x] = s;
+    for (int q = lane; q < S; q += 32) { const double v = red_buf[q * K + kk]; s = mx ? fmax(s, v) : s + v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double v = __shfl_xor_sync(kFull, s, o); s = mx ? fmax(s, v) : s + v; }
+    if (lane == 0) out[kk] = s;
   }
   __syncthreads();
 }
@@ -911,7 +924,8 @@ struct mde_solver {
   cudaGraph_t graph_u = nullptr;
   cudaGraphExec_t graph_exec_u = nullptr;
   int unroll = 1;
-  // mode 2: flat step graphs (one step / kStepsPerGraph steps), no conditional nodes
+  // mode 2: flat step graphs (one step / steps_per_graph steps), no conditional nodes
+  int steps_per_graph = 8;           // MDE_B200_STEPS (1..64)
   cudaGraph_t step_graph = nullptr, steps_graph = nullptr;
   cudaGraphExec_t step_exec = nullptr, steps_exec = nullptr;
   int step_kernels = 0;              // kernel nodes per step
@@ -1099,8 +1113,6 @@ int build_step_graph(mde_solver* s, int steps, cudaGraph_t* graph_out, cudaGraph
 #undef GTRY
 }
 
-constexpr int kStepsPerGraph = 8;
-
 // One iteration as a CUDA graph:
 //   fresh_gate -> IF(need_fresh){ evaluate at X } -> direction (P1,S1,P2,S2) -> WHILE(ls_active){ trial }
 //   -> accepted step + projection + iter_end.
@@ -1239,7 +1251,10 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
     TRY(cudaStreamSynchronize(st));
     rc = build_step_graph(s, 1, &s->step_graph, &s->step_exec);
     if (rc) goto fail;
-    rc = build_step_graph(s, kStepsPerGraph, &s->steps_graph, &s->steps_exec);
+    { const char* ev = getenv("MDE_B200_STEPS"); if (ev) s->steps_per_graph = atoi(ev); }
+    if (s->steps_per_graph < 1) s->steps_per_graph = 1;
+    if (s->steps_per_graph > 64) s->steps_per_graph = 64;
+    rc = build_step_graph(s, s->steps_per_graph, &s->steps_graph, &s->steps_exec);
     if (rc) goto fail;
   }
   if (opts->mode == 1) {
@@ -1323,15 +1338,16 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
     resume_kernel<<<1, 32, 0, st>>>(s->S, target);
     MDE_LAUNCH_CHECK();
     for (int round = 0;; ++round) {
-      if (round > (1 << 20)) return MDE_E_INVALID;
+      if (round > (1 << 18)) return MDE_E_INVALID;
       int remaining = target - s->host_iter;
       if (remaining < 1) remaining = 1;
       long long steps = 0;
-      if (remaining >= kStepsPerGraph) {
-        int graphs = (remaining + remaining / 8) / kStepsPerGraph;
-        if (graphs > 8) graphs = 8;
+      const int spg = s->steps_per_graph;
+      if (remaining >= spg) {
+        int graphs = (remaining + remaining / 8) / spg;
+        if (graphs * spg > 96) graphs = 96 / spg > 0 ? 96 / spg : 1;  // <= ~96 steps in flight per status read
         for (int b = 0; b < graphs; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->steps_exec, st));
-        steps = (long long)graphs * kStepsPerGraph;
+        steps = (long long)graphs * spg;
       } else {
         const int singles = remaining + remaining / 4 + (round > 0 ? 1 : 0);
         for (int b = 0; b < singles; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->step_exec, st));

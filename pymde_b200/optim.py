@@ -41,10 +41,12 @@ class SolveStats(object):
         p.text(self.__str__())
 
 
-# 1 = device-driven iterations (one CUDA graph per iteration: IF node for the fresh evaluation, WHILE node
-# for the line-search trials, scalars never leave the device); 0 = host-stepped line search (one 32-byte
-# status read per trial).  Edge-sharded multi-GPU solves use 0 (the NCCL hook is called from the host).
-DEFAULT_MODE = int(os.environ.get("PYMDE_B200_SOLVER_MODE", "1"))
+# 2 = flat CUDA graph of gated "steps" (one closure evaluation each; a device-side phase machine decides what
+# every kernel of the next step does, no conditional graph nodes, scalars never leave the device) -- default;
+# 1 = one CUDA graph per iteration with an IF node (fresh evaluation) and a WHILE node (line-search trials);
+# 0 = host-stepped line search (one status read per trial).  Edge-sharded multi-GPU solves use 0 (the NCCL
+# hook is called from the host).
+DEFAULT_MODE = int(os.environ.get("PYMDE_B200_SOLVER_MODE", "2"))
 
 
 class DeviceSolver(object):

@@ -15,7 +15,7 @@ ITERS = int(os.environ.get("VARIANT_ITERS", "400"))
 
 def run(cons, env):
     from pymde_b200 import optim
-    for k in ("MDE_B200_UNROLL",):
+    for k in ("MDE_B200_UNROLL", "MDE_B200_STEPS"):
         os.environ.pop(k, None)
     env = dict(env)
     optim.DEFAULT_MODE = int(env.pop("MODE", "1"))
@@ -33,7 +33,8 @@ def run(cons, env):
     return best, fe / done, avg[0], avg[-1], done
 
 
-VARIANTS = [{}, {"MDE_B200_UNROLL": "4"}, {"MODE": "2"}, {"MDE_B200_UNROLL": "4"}, {"MODE": "2"}]
+VARIANTS = [{"MODE": "1", "MDE_B200_UNROLL": "4"}, {"MODE": "2"}, {"MODE": "2", "MDE_B200_STEPS": "16"},
+            {"MODE": "2", "MDE_B200_STEPS": "32"}, {"MODE": "2"}]
 for cname, cons in (("centered", pm.Centered()), ("standardized", pm.Standardized())):
     for env in VARIANTS:
         tag = " ".join("%s=%s" % (k.replace("MDE_B200_", ""), v) for k, v in sorted(env.items())) or "mode1"
