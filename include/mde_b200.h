@@ -169,6 +169,9 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
 int mde_solver_destroy(mde_solver_t* s);
 /* Start a solve from X0 (device, (n,m)); copies it (MDE.embed clones, problem.py:448-449). */
 int mde_solver_begin(mde_solver_t* s, const float* X0, double eps, void* stream);
+/* Same, with this solve's iteration cap (1 <= max_iter <= opts.max_iter of mde_solver_create, which sizes the
+ * statistics buffers): one solver object serves embed() calls with different `max_iter`. */
+int mde_solver_begin_ex(mde_solver_t* s, const float* X0, double eps, int max_iter, void* stream);
 /* Run up to `iters` further iterations; stops early on convergence (||grad||_F <= eps,
  * optim.py:165).  Blocking.  On return *iters_done = total iterations so far,
  * *converged = 1 if the residual test fired.  Returns MDE_E_NAN where the reference raises

@@ -59,6 +59,7 @@ SIGNATURES = {
                                     C.POINTER(mde_solver_opts_t), C.c_void_p]),
     "mde_solver_destroy": (C.c_int, [C.c_void_p]),
     "mde_solver_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "mde_solver_begin_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]),
     "mde_solver_run": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "mde_solver_x": (C.c_void_p, [C.c_void_p]),
     "mde_solver_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

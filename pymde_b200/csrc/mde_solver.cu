@@ -930,6 +930,7 @@ struct mde_solver {
   cudaGraphExec_t step_exec = nullptr, steps_exec = nullptr;
   int step_kernels = 0;              // kernel nodes per step
   int host_iter = 0;                 // iterations completed (last status read)
+  int cur_max_iter = 0;              // iteration cap of the current solve (<= opts.max_iter)
   cudaStream_t cap_stream = nullptr, cap_stream2 = nullptr;
   cudaGraphConditionalHandle h_if = 0, h_while = 0, h_if_next = 0;  // capture-time only
   int graph_kernels_fixed = 0, graph_kernels_trial = 0, graph_kernels_fresh = 0;
@@ -1305,11 +1306,17 @@ int mde_solver_set_allreduce(mde_solver_t* s, mde_allreduce_fn fn, void* user) {
 }
 
 int mde_solver_begin(mde_solver_t* s, const float* X0, double eps, void* stream) {
+  return mde_solver_begin_ex(s, X0, eps, s ? s->opts.max_iter : 0, stream);
+}
+
+int mde_solver_begin_ex(mde_solver_t* s, const float* X0, double eps, int max_iter, void* stream) {
   if (!s || !X0) return MDE_E_INVALID;
+  if (max_iter < 1 || max_iter > s->opts.max_iter) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   MDE_CUDA_TRY(cudaMemcpyAsync(s->X, X0, sizeof(float) * s->N, cudaMemcpyDeviceToDevice, st));
-  const int mi = s->opts.max_iter;
-  init_state_kernel<<<1, 32, 0, st>>>(s->S, eps, s->opts.memory_size, mi, s->opts.world_size, s->stats,
+  const int mi = s->opts.max_iter;  // stride of the statistics arrays (capacity)
+  s->cur_max_iter = max_iter;
+  init_state_kernel<<<1, 32, 0, st>>>(s->S, eps, s->opts.memory_size, max_iter, s->opts.world_size, s->stats,
                                       s->stats + mi, s->stats + 2 * mi, s->stats + 3 * mi);
   MDE_LAUNCH_CHECK();
   s->host_need_fresh = 1;
@@ -1334,7 +1341,7 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
       return 0;
     }
     int target = s->host_iter + iters;
-    if (target > s->opts.max_iter) target = s->opts.max_iter;
+    if (target > s->cur_max_iter) target = s->cur_max_iter;
     resume_kernel<<<1, 32, 0, st>>>(s->S, target);
     MDE_LAUNCH_CHECK();
     for (int round = 0;; ++round) {

@@ -95,10 +95,13 @@ class DeviceSolver(object):
         except Exception:
             pass
 
-    def begin(self, X0, eps):
+    def begin(self, X0, eps, max_iter=None):
+        """Start a solve; `max_iter` (<= the capacity this solver was created with) caps this solve."""
         X0 = util.as_f32_cuda(X0, self.device)
+        cap = self.max_iter if max_iter is None else max(1, min(int(max_iter), self.max_iter))
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.mde_solver_begin(self.handle, X0.data_ptr(), float(eps), util.stream_ptr(self.device)))
+            _lib.check(self.lib.mde_solver_begin_ex(self.handle, X0.data_ptr(), float(eps), cap,
+                                                    util.stream_ptr(self.device)))
 
     def run(self, iters):
         done, conv = C.c_int(0), C.c_int(0)
@@ -163,7 +166,7 @@ def lbfgs(X, objective_fn, constraint, eps, max_iter, memory_size, use_line_sear
     layout = mde._layout()
     n, m = X.shape
     solver = mde._solver(constraint, memory_size, max_iter)
-    solver.begin(X, eps)
+    solver.begin(X, eps, max_iter)
     snapshots, times = [], []
     digits = len(str(max_iter))
     need_host_steps = verbose or snapshot_every is not None

@@ -261,14 +261,17 @@ class MDE(torch.nn.Module):
         return 1 <= int(memory_size) <= 32
 
     def _solver(self, constraint, memory_size, max_iter):
-        key = (id(constraint), int(memory_size), int(max_iter), optim.DEFAULT_MODE)
+        """Device solver for this problem, cached across embed() calls.  `max_iter` only sizes the statistics
+        buffers, so a cached solver with enough capacity is reused (its CUDA graphs are built once)."""
+        key = (id(constraint), int(memory_size), optim.DEFAULT_MODE)
         cur = self.__dict__["_device_solver"]
-        if cur is None or cur[0] != key:
+        if cur is None or cur[0] != key or cur[1].max_iter < int(max_iter):
             if cur is not None:
                 cur[1].close()
             dist = self.__dict__["_dist"]
+            capacity = max(int(max_iter), 1024)
             solver = optim.DeviceSolver(self._layout(), int(self.n_items), int(self.embedding_dim), constraint,
-                                        memory_size, max_iter,
+                                        memory_size, capacity,
                                         world_size=1 if dist is None else dist["world_size"],
                                         allreduce=None if dist is None else dist["allreduce"])
             cur = (key, solver)

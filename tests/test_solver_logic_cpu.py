@@ -57,10 +57,11 @@ def make_phi(kind, rng):
     return phi
 
 
+@pytest.mark.parametrize("seed", [0, 1000])
 @pytest.mark.parametrize("kind", ["quad", "quartic", "abs", "barrier", "steep"])
-def test_strong_wolfe_state_machine_matches_oracle(kind):
+def test_strong_wolfe_state_machine_matches_oracle(kind, seed):
     lib = _lib.load()
-    rng = np.random.default_rng(hash(kind) % 1000)
+    rng = np.random.default_rng({"quad": 11, "quartic": 23, "abs": 37, "barrier": 41, "steep": 53}[kind] + seed)
     checked = 0
     for _ in range(60):
         phi = make_phi(kind, rng)
@@ -78,7 +79,11 @@ def test_strong_wolfe_state_machine_matches_oracle(kind):
         assert err_c == err_ref
         if not err_ref:
             assert t_c == pytest.approx(float(t_ref), rel=2e-5, abs=1e-12), (kind, t0)
-            assert f_c == pytest.approx(float(f_ref), rel=1e-4, abs=1e-7)
+            # the accepted value is phi at the accepted step (the barrier is steep near its pole, so compare
+            # the values through the steps: equal steps to 2e-5 => values within the local slope times that)
+            assert f_c == pytest.approx(phi(t_c)[0], rel=1e-6, abs=1e-9)
+            slope = abs(float(phi(t_c)[1]))
+            assert abs(f_c - float(f_ref)) <= 1e-4 * abs(float(f_ref)) + 1e-7 + 4e-5 * slope * abs(t_c)
         checked += 1
     assert checked > 20
 
