@@ -620,6 +620,16 @@ __global__ void anchor_rows_kernel(const int* flag, float* __restrict__ Z, const
   Z[a * m + (i % m)] = values ? values[i] : 0.0f;
 }
 
+// mode 2, multi-GPU: the all-reduced [gradient | loss] becomes the solver's gradient buffer -- only when the
+// step really evaluated (the all-reduce itself cannot be gated, so it works on a staging buffer)
+__global__ void __launch_bounds__(kVecThreads)
+gated_copy_kernel(const int* flag, const float* __restrict__ src, float* __restrict__ dst, int64_t n4) {
+  if (off(flag)) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+}
+
 // multi-GPU: pack this rank's loss sum behind the gradient as (hi, lo) floats
 __global__ void __launch_bounds__(256)
 pack_loss_kernel(const int* flag, const double* __restrict__ lpart, int nl, float* __restrict__ tail) {
@@ -902,6 +912,7 @@ struct mde_solver {
   SolverState* S = nullptr;          // device
   int* status_host = nullptr;        // pinned, kStatusInts ints
   float *X = nullptr, *xinit = nullptr, *d = nullptr, *g = nullptr, *gprev = nullptr, *Sb = nullptr, *Yb = nullptr;
+  float* gpart = nullptr;            // mode 2, multi-GPU: this rank's partial [gradient | loss] before the all-reduce
   double *dpart = nullptr;           // dot partials
   double *stats = nullptr;           // 4 * max_iter doubles
   void* projws = nullptr;
@@ -975,19 +986,28 @@ Tail make_tail(mde_solver* s, int mode) {
 }
 
 int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cudaStream_t st) {
+  // mode 2 on several GPUs: scatter into the staging buffer, all-reduce it (unconditionally -- the host does
+  // not know the phase), then copy it into g under the evaluation gate
+  const bool staged = (s->opts.mode == 2 && s->opts.world_size > 1);
+  float* target = staged ? s->gpart : s->g;
   if (zero_g) {
     const int64_t n4 = (s->npad + 4) >> 2;  // gradient + (hi, lo) tail
-    zero_kernel<<<vec_blocks(n4), kVecThreads, 0, st>>>(flag, s->g, n4);
+    zero_kernel<<<vec_blocks(n4), kVecThreads, 0, st>>>(flag, target, n4);
     MDE_LAUNCH_CHECK();
   }
-  int rc = distortion_fused_flag(s->edges, s->X, s->m, s->g, &s->nl, flag, st);
+  int rc = distortion_fused_flag(s->edges, s->X, s->m, target, &s->nl, flag, st);
   if (rc) return rc;
   if (s->opts.world_size > 1) {
-    pack_loss_kernel<<<1, 256, 0, st>>>(flag, loss_partials_ptr(s->edges), s->nl, s->g + s->npad);
+    pack_loss_kernel<<<1, 256, 0, st>>>(flag, loss_partials_ptr(s->edges), s->nl, target + s->npad);
     MDE_LAUNCH_CHECK();
     if (!s->allreduce) return MDE_E_INVALID;
-    rc = s->allreduce(s->allreduce_user, s->g, s->npad + 4, (void*)st);
+    rc = s->allreduce(s->allreduce_user, target, s->npad + 4, (void*)st);
     if (rc) return rc;
+    if (staged) {
+      const int64_t n4 = (s->npad + 4) >> 2;
+      gated_copy_kernel<<<vec_blocks(n4), kVecThreads, 0, st>>>(flag, s->gpart, s->g, n4);
+      MDE_LAUNCH_CHECK();
+    }
   }
   const int* act = flag;
   if (s->opts.constraint == MDE_CONSTRAINT_STANDARDIZED) {
@@ -1074,7 +1094,8 @@ int enqueue_step(mde_solver* s, cudaStream_t st) {
   SolverState* S = s->S;
   int rc = enqueue_direction(s, st, &S->g_dir);
   if (rc) return rc;
-  step_axpy_kernel<<<s->nvb, kVecThreads, 0, st>>>(S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m, s->g);
+  step_axpy_kernel<<<s->nvb, kVecThreads, 0, st>>>(S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m,
+                                                   s->opts.world_size > 1 ? s->gpart : s->g);
   MDE_LAUNCH_CHECK();
   switch (s->opts.constraint) {  // retraction of the moved iterate (project_callback, lbfgs.py:368-372)
     case MDE_CONSTRAINT_CENTERED:
@@ -1210,7 +1231,7 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   if (opts->constraint < 0 || opts->constraint > MDE_CONSTRAINT_ANCHORED) return MDE_E_INVALID;
   if (opts->max_iter < 1) return MDE_E_INVALID;
   if (opts->mode < 0 || opts->mode > 2) return MDE_E_INVALID;
-  if (opts->mode != 0 && opts->world_size > 1) return MDE_E_UNSUPPORTED;  // NCCL hook is host-stepped
+  if (opts->mode == 1 && opts->world_size > 1) return MDE_E_UNSUPPORTED;  // the NCCL hook is called from the host
   if (n != edges_n(e)) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   mde_solver* s = new (std::nothrow) mde_solver();
@@ -1224,6 +1245,7 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   TRY(cudaMallocHost(&s->status_host, kStatusInts * sizeof(int)));
   TRY(cudaMalloc(&s->X, vb)); TRY(cudaMalloc(&s->xinit, vb)); TRY(cudaMalloc(&s->d, vb));
   TRY(cudaMalloc(&s->g, vb)); TRY(cudaMalloc(&s->gprev, vb));
+  if (opts->mode == 2 && opts->world_size > 1) { TRY(cudaMalloc(&s->gpart, vb)); TRY(cudaMemsetAsync(s->gpart, 0, vb, st)); }
   TRY(cudaMalloc(&s->Sb, (int64_t)(opts->memory_size + 1) * s->npad * sizeof(float)));
   TRY(cudaMalloc(&s->Yb, (int64_t)(opts->memory_size + 1) * s->npad * sizeof(float)));
   TRY(cudaMalloc(&s->dpart, sizeof(double) * (int64_t)kVecBlocks * kDotsPerSlice * kMaxSlices));
@@ -1246,8 +1268,8 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   s->nvb = vec_blocks(s->npad >> 2);
   if (opts->constraint == MDE_CONSTRAINT_CENTERED && (m == 1 || m == 2 || m == 4)) s->center_m = m;
   { const char* ev = getenv("MDE_B200_FUSE"); if (ev && ev[0] == '0') s->fuse = 0; }
-  if (opts->mode == 2) {
-    s->fuse = 1;  // the phase machine lives in the fused epilogues
+  if (opts->mode == 2) s->fuse = 1;  // the phase machine lives in the fused epilogues
+  if (opts->mode == 2 && opts->world_size == 1) {  // several GPUs: steps are stream launches (NCCL hook between)
     s->nl = 0;
     TRY(cudaStreamSynchronize(st));
     rc = build_step_graph(s, 1, &s->step_graph, &s->step_exec);
@@ -1282,7 +1304,7 @@ fail:
 int mde_solver_destroy(mde_solver_t* s) {
   if (!s) return 0;
   cudaFree(s->S); cudaFreeHost(s->status_host);
-  cudaFree(s->X); cudaFree(s->xinit); cudaFree(s->d); cudaFree(s->g); cudaFree(s->gprev);
+  cudaFree(s->X); cudaFree(s->xinit); cudaFree(s->d); cudaFree(s->g); cudaFree(s->gprev); cudaFree(s->gpart);
   cudaFree(s->Sb); cudaFree(s->Yb); cudaFree(s->dpart); cudaFree(s->stats); cudaFree(s->projws);
   cudaFree(s->anchors); cudaFree(s->anchor_values);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -1350,7 +1372,12 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
       if (remaining < 1) remaining = 1;
       long long steps = 0;
       const int spg = s->steps_per_graph;
-      if (remaining >= spg) {
+      if (s->opts.world_size > 1) {
+        // every rank enqueues the same number of steps (same `remaining`: the replicated state machines agree)
+        int n_steps = remaining + remaining / 8 + (round > 0 ? 1 : 0);
+        if (n_steps > 64) n_steps = 64;
+        for (int b = 0; b < n_steps; ++b) { if ((rc = enqueue_step(s, st))) return rc; }
+      } else if (remaining >= spg) {
         int graphs = (remaining + remaining / 8) / spg;
         if (graphs * spg > 96) graphs = 96 / spg > 0 ? 96 / spg : 1;  // <= ~96 steps in flight per status read
         for (int b = 0; b < graphs; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->steps_exec, st));
@@ -1360,7 +1387,7 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
         for (int b = 0; b < singles; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->step_exec, st));
         steps = singles;
       }
-      g_launch_count += (unsigned long long)steps * s->step_kernels;
+      g_launch_count += (unsigned long long)steps * s->step_kernels;  // (stream-launched steps count themselves)
       if ((rc = read_status(s, st))) return rc;
       s->host_iter = s->status_host[2];
       if (s->status_host[3]) { s->host_active = 0; if (iters_done) *iters_done = s->status_host[2]; return s->status_host[3]; }

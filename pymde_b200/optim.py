@@ -62,7 +62,9 @@ class DeviceSolver(object):
         opts.constraint = int(constraint._solver_id)
         opts.memory_size = int(memory_size)
         opts.max_iter = max(int(max_iter), 1)
-        opts.mode = (DEFAULT_MODE if mode is None else int(mode)) if int(world_size) == 1 else 0
+        opts.mode = DEFAULT_MODE if mode is None else int(mode)
+        if int(world_size) > 1 and opts.mode == 1:  # conditional-node graphs cannot host the NCCL hook
+            opts.mode = 0
         opts.world_size = int(world_size)
         self.mode = opts.mode
         self._keep = []
