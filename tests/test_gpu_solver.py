@@ -258,3 +258,45 @@ def test_wide_embeddings_follow_the_oracle(m, cname):
     np.testing.assert_allclose(mde.solve_stats.average_distortions[:k], st.average_distortions[:k], rtol=2e-3)
     np.testing.assert_allclose(mde.solve_stats.residual_norms[0], st.residual_norms[0], rtol=1e-4)
     assert mde.solve_stats.average_distortions[-1] < mde.solve_stats.average_distortions[0]
+
+
+def test_one_solver_serves_embeds_with_different_max_iter(golden):
+    """max_iter only sizes statistics: the cached device solver (and its CUDA graphs) is reused, and a solve
+    capped at k iterations is the prefix of a longer one (docs5 is evaluated without atomics races)."""
+    import pymde_b200 as pm
+    g = golden["trajectories"]
+    mde, X0 = build(pm, "docs5", g)
+    mde.embed(X=X0.clone(), max_iter=4, eps=0.0)
+    s4 = mde.solve_stats
+    solver = mde.__dict__["_device_solver"][1]
+    mde.embed(X=X0.clone(), max_iter=9, eps=0.0)
+    s9 = mde.solve_stats
+    assert mde.__dict__["_device_solver"][1] is solver
+    assert s4.iterations == 4 and s9.iterations == 9
+    assert list(s9.average_distortions[:4]) == list(s4.average_distortions)
+    assert list(s9.residual_norms[:4]) == list(s4.residual_norms)
+
+
+def test_pause_and_resume_is_exact(golden, solver_mode):
+    """run(3) + run(4) + run(5) == run(12): pausing at an iteration boundary does not perturb the solve."""
+    import pymde_b200 as pm
+    g = golden["trajectories"]
+    res = []
+    for chunks in ((12,), (3, 4, 5)):
+        mde, X0 = build(pm, "docs5", g)
+        solver = mde._solver(mde.constraint, 10, 64)
+        solver.begin(X0, 0.0, 12)
+        done = 0
+        for c in chunks:
+            done, conv = solver.run(c)
+        assert done == 12
+        avg, resid, pct, stp, fe = solver.stats(done)
+        res.append((avg.copy(), resid.copy(), stp.copy(), fe, solver.x_view().clone()))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    assert res[0][3] == res[1][3]
+    assert torch.equal(res[0][4], res[1][4])
+    # a further run() after the cap is a no-op
+    d2, _ = solver.run(5)
+    assert d2 == 12
