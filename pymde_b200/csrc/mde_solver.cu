@@ -354,10 +354,13 @@ __device__ void lbfgs_direction_block(LbfgsState& B, double* dots, double ys, do
     //   loop 2 (oldest -> newest):  c_i = al_i - (H (Y^T q)_i + sum_{j<i} c_j SY[j][i]) / SY[i][i]
     const int lane = tid, h = B.count;
     const double H = B.H_diag;
+    // fp64 division is a ~300-cycle software routine: take the h reciprocals of the pivots in parallel (one per
+    // lane) so that the two dependent chains below are shuffle + multiply + FMA only
+    const double inv_piv = (lane < h) ? 1.0 / B.SY[lane][lane] : 0.0;
     double rhs = (lane < h) ? -sj_g[lane] : 0.0;
     double al = 0.0;
     for (int i = h - 1; i >= 0; --i) {
-      const double ali = __shfl_sync(kFull, rhs, i) / B.SY[i][i];
+      const double ali = __shfl_sync(kFull, rhs, i) * __shfl_sync(kFull, inv_piv, i);
       if (lane == i) al = ali;
       if (lane < i) rhs -= ali * B.SY[lane][i];
     }
@@ -371,7 +374,7 @@ __device__ void lbfgs_direction_block(LbfgsState& B, double* dots, double ys, do
     for (int j = 0; j < h; ++j) {
       const double accj = __shfl_sync(kFull, acc, j);
       const double alj = __shfl_sync(kFull, al, j);
-      const double ccj = alj - accj / B.SY[j][j];
+      const double ccj = alj - accj * __shfl_sync(kFull, inv_piv, j);
       if (lane == j) cc = ccj;
       if (lane > j && lane < h) acc += ccj * B.SY[j][lane];
     }
