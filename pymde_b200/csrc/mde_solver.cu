@@ -392,20 +392,35 @@ __device__ void direction_scalar_body(SolverState* __restrict__ S, const double*
   int* flags = reinterpret_cast<int*>(dots + 5 * kSlots);
   static_assert(sizeof(LbfgsState) % sizeof(double) == 0, "LbfgsState must be a whole number of doubles");
   static_assert(kMaxMemory <= 32, "the two-loop recursion maps one pair per lane");
+  // The history state is staged through registers so that its loads are in flight together with the loads of
+  // the reductions below (both come from L2; issuing them back to back hides one round trip).
+  constexpr int kStateDoubles = (int)(sizeof(LbfgsState) / sizeof(double));
+  constexpr int kStatePerThread = (kStateDoubles + 255) / 256;
+  const int count = S->lb.count;
+  const int n_iter = S->lb.n_iter;
+  double stage[kStatePerThread];
   {
     const double* src = reinterpret_cast<const double*>(&S->lb);
-    double* dst = reinterpret_cast<double*>(&sB);
-    for (int k = threadIdx.x; k < (int)(sizeof(LbfgsState) / sizeof(double)); k += blockDim.x) dst[k] = src[k];
+#pragma unroll
+    for (int q = 0; q < kStatePerThread; ++q) {
+      const int k = (int)threadIdx.x + q * 256;
+      stage[q] = (threadIdx.x < 256 && k < kStateDoubles) ? __ldcg(src + k) : 0.0;
+    }
   }
-  __syncthreads();
-  const int count = sB.count;
-  const int n_iter = sB.n_iter;
   int slices = (count + kPairsPerSlice - 1) / kPairsPerSlice;
   if (slices < 1) slices = 1;
   if (n_iter > 0) {
     for (int s = 0; s < slices; ++s)
       reduce_partials<false>(part + (int64_t)s * nblocks * kDotsPerSlice, nblocks, kDotsPerSlice,
                              sums + s * kDotsPerSlice);
+  }
+  {
+    double* dst = reinterpret_cast<double*>(&sB);
+#pragma unroll
+    for (int q = 0; q < kStatePerThread; ++q) {
+      const int k = (int)threadIdx.x + q * 256;
+      if (threadIdx.x < 256 && k < kStateDoubles) dst[k] = stage[q];
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -702,14 +717,78 @@ __device__ double eval_loss(const SolverState* S, const double* lpart, int nl, c
   return (double)(float)(sum / p_total);
 }
 
+// Both reductions an evaluation needs in ONE pass: loss partials of the scatter launch (nl x 1) and the
+// (g.d, g.g, |g|_1) partials of the dots pass (nd x 3).  Same thread mapping and summation order as two
+// reduce_partials calls (bit-identical results), but the loads of both are in flight together and there
+// are two block barriers instead of four.  blockDim.x == 256.  out4 = [loss sum, g.d, g.g, |g|_1].
+__device__ void reduce_loss_and_dots(const double* __restrict__ lpart, int nl, const double* __restrict__ dpart,
+                                     int nd, double* out4) {
+  __shared__ double buf_a[256], buf_b[256];
+  constexpr int U = 4, SB = 85;  // 85 segments x 3 outputs = 255 threads for the dots
+  const int t = threadIdx.x;
+  const int kb = t % 3, segb = t / 3;
+  const bool useb = t < 3 * SB;
+  double a = 0.0, b = 0.0;
+  for (int it = 0;; ++it) {
+    const int ia0 = t + it * U * 256, ib0 = segb + it * U * SB;
+    if (ia0 >= nl && (!useb || ib0 >= nd)) break;
+    double va[U], vb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int i = ia0 + u * 256; va[u] = (i < nl) ? __ldcg(lpart + i) : 0.0; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = ib0 + u * SB;
+      vb[u] = (useb && i < nd) ? __ldcg(dpart + (int64_t)i * 3 + kb) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) a += va[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) b += vb[u];
+  }
+  buf_a[t] = a;
+  buf_b[t] = b;  // index seg * 3 + k == t for t < 255
+  __syncthreads();
+  const int lane = t & 31, w = t >> 5;
+  if (w == 0) {
+    double v = 0.0;
+    for (int q = lane; q < 256; q += 32) v += buf_a[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if (lane == 0) out4[0] = v;
+  } else if (w <= 3) {
+    const int k = w - 1;
+    double v = 0.0;
+    for (int q = lane; q < SB; q += 32) v += buf_b[q * 3 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if (lane == 0) out4[1 + k] = v;
+  }
+  __syncthreads();
+}
+
+// loss and (g.d, g.g, |g|_1) of one evaluation -> out3[0..2], returns the loss as the reference sees it
+__device__ double eval_reductions(const SolverState* S, const double* lpart, int nl, const float* tail,
+                                  const double* dpart, int nd, double p_total, double* out3) {
+  __shared__ double r4[4];
+  if (S->world > 1 || blockDim.x != 256) {
+    __shared__ double l1[1];
+    const double loss = eval_loss(S, lpart, nl, tail, l1, p_total);
+    reduce_partials<false>(dpart, nd, 3, out3);
+    return loss;
+  }
+  reduce_loss_and_dots(lpart, nl, dpart, nd, r4);
+  if (threadIdx.x < 3) out3[threadIdx.x] = r4[1 + threadIdx.x];
+  const double loss = (double)(float)(r4[0] / p_total);
+  __syncthreads();
+  return loss;
+}
+
 // S(fresh): closure() at the current iterate (lbfgs.py:426), no line search involved
 __device__ void fresh_finish_body(SolverState* __restrict__ S, const double* __restrict__ lpart, int nl,
                                   const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
                                   double p_total) {
   __shared__ double out[3];
-  __shared__ double l1[1];
-  double loss = eval_loss(S, lpart, nl, tail, l1, p_total);
-  reduce_partials<false>(dpart, nd, 3, out);
+  const double loss = eval_reductions(S, lpart, nl, tail, dpart, nd, p_total, out);
   if (threadIdx.x == 0) {
     S->loss = loss; S->gg = out[1]; S->g1 = out[2];
     S->func_evals += 1;
@@ -729,9 +808,7 @@ __device__ void ls_update_body(SolverState* __restrict__ S, const double* __rest
                                const float* __restrict__ tail, const double* __restrict__ dpart, int nd,
                                double p_total, cudaGraphConditionalHandle h_while) {
   __shared__ double out[3];
-  __shared__ double l1[1];
-  double loss = eval_loss(S, lpart, nl, tail, l1, p_total);
-  reduce_partials<false>(dpart, nd, 3, out);
+  const double loss = eval_reductions(S, lpart, nl, tail, dpart, nd, p_total, out);
   if (threadIdx.x == 0) {
     S->gg = out[1]; S->g1 = out[2];
     S->func_evals += 1;
