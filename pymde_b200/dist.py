@@ -5,8 +5,6 @@ E and grad E are sums over edges (pymde/average_distortion.py:51,77-78), so each
 same fused kernel on its shard with the GLOBAL edge count as divisor; after the all-reduce
 every rank holds bit-identical gradient and loss, the device-resident L-BFGS state is
 replicated and (thanks to fixed-order reductions) takes identical decisions on every rank."""
-import ctypes as C
-
 import torch
 import torch.distributed as dist
 
