@@ -2,8 +2,6 @@
 
 Class names and constructor signatures follow pymde/functions/losses.py:61-239; the bodies are
 table entries for the CUDA kernels (pymde_b200/csrc/mde_common.cuh::eval_fn)."""
-import torch
-
 from .. import util
 from .function import Function
 
