@@ -10,7 +10,7 @@ from . import constraints, functions, optim, util  # noqa: F401
 from .constraints import Anchored, Centered, Standardized  # noqa: F401
 from .functions import losses, penalties  # noqa: F401
 from .problem import MDE  # noqa: F401
-from .util import align, all_edges, center, seed  # noqa: F401
+from .util import align, all_edges, center, rotate, seed  # noqa: F401
 
 
 def __getattr__(name):
@@ -22,6 +22,7 @@ def __getattr__(name):
     if name in ("preprocess", "Graph"):
         preprocess = importlib.import_module(__name__ + ".preprocess")
         return preprocess if name == "preprocess" else preprocess.Graph
-    if name == "quadratic":
-        return importlib.import_module(__name__ + ".quadratic")
+    if name in ("quadratic", "pca"):
+        quadratic = importlib.import_module(__name__ + ".quadratic")
+        return quadratic if name == "quadratic" else quadratic.pca
     raise AttributeError("module 'pymde_b200' has no attribute %r" % name)

@@ -89,6 +89,44 @@ class Logistic(_Weighted):
         return (float(self.threshold), float(self.alpha), 0.0)
 
 
+class _TorchPenalty(_Weighted):
+    """Penalties the reference ships without documentation (pymde/functions/penalties.py:269-307).  They are not
+    in the kernels' function table: an MDE using them evaluates f and f' with torch on the per-edge distances the
+    CUDA path produces and scatters the result with `mde_scatter_external`, like any user-defined callable."""
+
+    def _supported(self):
+        return False
+
+
+class Sigmoid(_TorchPenalty):
+    """f(d) = w * sigmoid(alpha (d - threshold))"""
+
+    def __init__(self, weights, threshold, alpha=1.0):
+        if threshold < 0:
+            raise ValueError("Threshold must be nonnegative, received ", threshold)
+        super(Sigmoid, self).__init__(weights)
+        self.threshold = threshold
+        self.alpha = alpha
+
+    def forward(self, distances):
+        return self.weights * torch.sigmoid(self.alpha * (distances - self.threshold))
+
+
+class Hinge(_TorchPenalty):
+    """f(d) = max(0, w * (d - (threshold - sign(w) * sigma))), sigma defaults to threshold / 2"""
+
+    def __init__(self, weights, threshold, sigma=None):
+        if threshold < 0:
+            raise ValueError("Threshold must be nonnegative, received ", threshold)
+        super(Hinge, self).__init__(weights)
+        self.threshold = threshold
+        self.sigma = threshold / 2 if sigma is None else sigma
+
+    def forward(self, distances):
+        knee = self.threshold - torch.sign(self.weights) * self.sigma
+        return torch.clamp(self.weights * (distances - knee), min=0.0)
+
+
 class Log1p(_WithExponent):
     """p(d) = log(1 + d^exponent)"""
     _fn_id = 7

@@ -26,7 +26,7 @@ def _laplacian(n, edges, weights):
     return sp.diags(np.asarray(A.sum(1)).ravel()) - A
 
 
-def spectral(n_items, embedding_dim, edges, weights, max_iter=1000, device=None, cg=False):
+def spectral(n_items, embedding_dim, edges, weights, cg=False, max_iter=1000, device=None):
     """Standardized spectral embedding: eigenvectors 2..m+1 of L = D - W (quadratic.py:122-179)."""
     L = _laplacian(int(n_items), edges, weights)
     k = int(embedding_dim) + 1

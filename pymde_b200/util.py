@@ -10,6 +10,7 @@ import torch
 from . import _lib
 
 _NP_RNG = np.random.default_rng()
+_DEFAULT_DEVICE = "cuda"  # see get_default_device / set_default_device
 
 
 class SolverError(Exception):
@@ -19,7 +20,7 @@ class SolverError(Exception):
 def cuda_device(device=None):
     """Canonical CUDA device.  None -> current CUDA device.  CPU devices are rejected loudly."""
     if device is None:
-        device = "cuda"
+        device = _DEFAULT_DEVICE
     dev = torch.device(device) if not isinstance(device, torch.device) else device
     if dev.type != "cuda":
         raise ValueError(
@@ -107,6 +108,74 @@ def align(source, target):
     tgt = tgt / tgt.norm(dim=0)
     Q = procrustes(src, tgt)
     return (src @ Q) * rms[None, :] + mu
+
+
+def rotate(X, degrees):
+    """Rotate a 2-D embedding by `degrees` (scalar) or a 3-D one by three angles: about the x axis first, then
+    y, then z (pymde/util.py:255-288; row vectors, X @ R)."""
+    X = to_tensor(X)
+    degrees = to_tensor(degrees).to(X.device)
+    if X.shape[1] not in (2, 3):
+        raise ValueError("Only 2 or 3 dimensional embeddings can be rotated using this method.")
+    rad = torch.deg2rad(degrees.float().reshape(-1))
+    c, s = torch.cos(rad), torch.sin(rad)
+    if X.shape[1] == 2:
+        if rad.numel() != 1:
+            raise ValueError("`degrees` must be a scalar.")
+        R = torch.stack([torch.stack([c[0], -s[0]]), torch.stack([s[0], c[0]])])
+        return X @ R.to(X.dtype)
+    if rad.numel() != 3:
+        raise ValueError("`degrees` must be a length-3 tensor.")
+    one, zero = torch.ones_like(c[0]), torch.zeros_like(c[0])
+    Rx = torch.stack([torch.stack([one, zero, zero]), torch.stack([zero, c[0], s[0]]), torch.stack([zero, -s[0], c[0]])])
+    Ry = torch.stack([torch.stack([c[1], zero, -s[1]]), torch.stack([zero, one, zero]), torch.stack([s[1], zero, c[1]])])
+    Rz = torch.stack([torch.stack([c[2], s[2], zero]), torch.stack([-s[2], c[2], zero]), torch.stack([zero, zero, one])])
+    return X @ (Rx @ Ry @ Rz).to(X.dtype)
+
+
+def in_stdemb(X):
+    """True when X is centered with (1/n) X^T X = I (pymde/util.py:121-126; any embedding dimension here)."""
+    X = to_tensor(X)
+    cov = (1.0 / X.shape[0]) * X.T @ X
+    eye = torch.eye(X.shape[1], dtype=X.dtype, device=X.device)
+    return bool(torch.isclose(cov, eye).all() and torch.isclose(X.mean(dim=0), torch.zeros_like(cov[0])).all())
+
+
+def random_edges(n, p, seed=0):
+    """p distinct uniformly random pairs i < j (pymde/util.py:411-422): indices into the row-major upper
+    triangle drawn without replacement, mapped back to (i, j) by the closed-form inverse."""
+    n, p = int(n), int(p)
+    idx = np.random.default_rng(seed).choice(n * (n - 1) // 2, p, replace=False, shuffle=False).astype(np.float64)
+    i = n - 2 - np.floor(np.sqrt(-8.0 * idx + 4.0 * n * (n - 1) - 7.0) / 2.0 - 0.5)
+    j = idx + i + 1 - n * (n - 1) / 2 + (n - i) * ((n - i) - 1) / 2
+    return torch.tensor(np.stack([i, j], axis=1).astype(np.int64))
+
+
+def adjacency_matrix(n, m, edges, weights, use_scipy=True):
+    """Symmetric weighted adjacency matrix A + A^T of the edge list (pymde/util.py:174-198); `m` is unused, as in
+    the reference.  scipy COO by default, torch sparse COO otherwise."""
+    del m
+    if use_scipy:
+        import scipy.sparse
+        w = weights.detach().cpu().numpy() if isinstance(weights, torch.Tensor) else np.asarray(weights)
+        e = edges.detach().cpu().numpy() if isinstance(edges, torch.Tensor) else np.asarray(edges)
+        A = scipy.sparse.coo_matrix((w, (e[:, 0], e[:, 1])), shape=(n, n), dtype=np.float32)
+        return (A + A.T).tocoo()
+    A = torch.sparse_coo_tensor(edges.transpose(0, 1), weights, size=(n, n), dtype=torch.float32, device=edges.device)
+    return A + A.transpose(0, 1)
+
+
+def get_default_device():
+    """Device recipes use when none is given (pymde/util.py:20-37).  Always a CUDA device here."""
+    return str(_DEFAULT_DEVICE)
+
+
+def set_default_device(device):
+    global _DEFAULT_DEVICE
+    dev = torch.device(device) if not isinstance(device, torch.device) else device
+    if dev.type != "cuda":
+        raise ValueError("pymde_b200 runs on CUDA devices only; got %r" % (device,))
+    _DEFAULT_DEVICE = dev
 
 
 def scale_delta(delta, d_nat):
