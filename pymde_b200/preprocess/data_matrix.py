@@ -9,6 +9,7 @@ import torch
 
 from .. import util
 from .graph import Graph
+from .preprocess import sample_edges  # noqa: F401  (the reference exposes it here as well)
 
 
 def _to_device_matrix(data, device):
@@ -42,7 +43,6 @@ def k_nearest_neighbors(data, k, max_distance=None, verbose=False, device=None, 
 
 def distances(data, retain_fraction=1.0, verbose=False, device=None):
     """Graph of pairwise Euclidean distances: all (n choose 2) pairs, or a uniform sample of them."""
-    from .preprocess import sample_edges
     dev = util.cuda_device(device)
     X = _to_device_matrix(data, dev)
     n = X.shape[0]

@@ -90,6 +90,26 @@ class Graph(object):
     def neighbor_distances(self, node):
         return self._A.data[self._A.indptr[node]:self._A.indptr[node + 1]]
 
+    def draw(self, embedding_dim=2, standardized=False, device=None, verbose=False):
+        """Embed the graph for drawing (pymde/preprocess/graph.py:200-256): shortest-path distances (at most 1e7
+        of them), WeightedQuadratic loss + Centered, or Cubic penalty + Standardized.  Returns the embedding;
+        plotting is out of scope here."""
+        from .. import constraints, problem
+        from ..functions import losses, penalties
+        if bool((self.distances < 0).any()):
+            raise ValueError("Graphs with negative edge weights cannot be drawn.")
+        if self.n_edges < self.n_all_edges:
+            dg = shortest_paths(self, retain_fraction=min(1.0, 1e7 / self.n_all_edges), verbose=verbose)
+        else:
+            dg = self
+        if not standardized:
+            constraint, f = constraints.Centered(), losses.WeightedQuadratic(dg.distances)
+        else:
+            constraint, f = constraints.Standardized(), penalties.Cubic(1 / dg.distances)
+        mde = problem.MDE(n_items=self.n_items, embedding_dim=embedding_dim, edges=dg.edges, distortion_function=f,
+                          constraint=constraint, device=device)
+        return mde.embed(verbose=verbose)
+
     def __getitem__(self, key):
         return self._A[key]
 
@@ -97,9 +117,18 @@ class Graph(object):
         raise AttributeError("Graph objects are immutable.")
 
 
-def shortest_paths(graph, max_length=None, n_workers=None, verbose=False):
-    """All-pairs shortest-path distances as a Graph (unreachable / beyond max_length pairs dropped).
-    Unweighted graphs use BFS hop counts, weighted ones Dijkstra (scipy.sparse.csgraph)."""
+def shortest_paths(graph, max_length=None, retain_fraction=1.0, n_workers=None, verbose=False):
+    """Shortest-path distances as a Graph (interface of pymde/preprocess/graph.py:345-474): unreachable pairs and
+    pairs beyond `max_length` are dropped; with `retain_fraction` < 1 every remaining pair is kept with that
+    probability (Bernoulli draws from the module RNG seeded by `pymde_b200.seed`, like the reference's per-row
+    sampling), which bounds memory on large graphs.  Unweighted graphs use BFS hop counts, weighted ones Dijkstra
+    (scipy.sparse.csgraph), in row chunks."""
+    from .. import util
+    del n_workers
+    if sp.issparse(graph):
+        graph = Graph(graph)
+    elif not isinstance(graph, Graph):
+        raise ValueError("`graph` must be a pymde.Graph instance or scipy.sparse adjacency matrix.")
     A = graph.adjacency_matrix
     unweighted = bool((A.data == 1.0).all())
     limit = np.inf if max_length is None else float(max_length)
@@ -111,9 +140,33 @@ def shortest_paths(graph, max_length=None, n_workers=None, verbose=False):
         D = csgraph.dijkstra(A, directed=False, indices=idx, unweighted=unweighted, limit=limit)
         r, c = np.nonzero(np.isfinite(D) & (D > 0))
         keep = c > idx[r]
+        if retain_fraction < 1.0:
+            keep &= util.np_rng().uniform(size=keep.size) <= retain_fraction
         rows.append(idx[r][keep]); cols.append(c[keep]); vals.append(D[r, c][keep])
     rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
     return Graph.from_edges(np.stack([rows, cols], 1), vals.astype(np.float32), n_items=n)
+
+
+def scale(graph, natural_length):
+    """New graph whose distances have RMS `natural_length` (pymde/preprocess/graph.py:259-279)."""
+    d = graph.distances
+    alpha = float(natural_length) / float(d.pow(2).mean().sqrt())
+    return Graph.from_edges(graph.edges, alpha * d, n_items=graph.n_items)
+
+
+def breadth_first_order(csgraph_matrix, i_start, directed=True, return_predecessors=True):
+    """Hop counts from `i_start` (inf where unreachable) and BFS predecessors (-9999 where none), the pair the
+    reference's Cython helper returns (pymde/preprocess/graph.py:286-308)."""
+    del return_predecessors
+    order, pred = csgraph.breadth_first_order(csgraph_matrix, i_start, directed=directed, return_predecessors=True)
+    n = csgraph_matrix.shape[0]
+    lengths = np.full(n, np.inf, dtype=np.float32)
+    lengths[i_start] = 0.0
+    for v in order[1:]:  # BFS order: a node's predecessor is always settled before the node
+        lengths[v] = lengths[pred[v]] + 1.0
+    pred = pred.astype(np.int32)
+    pred[pred < 0] = -9999
+    return lengths, pred
 
 
 def k_nearest_neighbors(graph, k, graph_distances=False, max_distance=None, verbose=False):

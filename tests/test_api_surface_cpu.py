@@ -66,6 +66,11 @@ def test_public_names_exist(ref):
         obj = getattr(ref, name)
         if inspect.isfunction(obj) or inspect.isclass(obj):
             assert hasattr(pm, name), name
+    assert hasattr(pm.Graph, "draw") and hasattr(pm.preprocess, "generic")
+    for name in ("scale", "shortest_paths", "k_nearest_neighbors", "breadth_first_order", "Graph"):
+        assert hasattr(pm.preprocess.graph, name), name
+    assert _params(ref.preprocess.graph.shortest_paths) == _params(pm.preprocess.graph.shortest_paths)
+    assert _params(ref.Graph.draw) == _params(pm.Graph.draw)
     for mod in ("penalties", "losses", "constraints", "preprocess", "recipes", "quadratic"):
         r, o = getattr(ref, mod), getattr(pm, mod)
         for name in dir(r):

@@ -91,3 +91,33 @@ def test_spectral_initialisation_is_standardized_and_spectral():
     d2 = (X[e[:, 0]] - X[e[:, 1]]).pow(2).sum(1)
     lam = 2.0 * (1.0 - np.cos(2.0 * np.pi / n))  # smallest non-zero Laplacian eigenvalue of the cycle (double)
     np.testing.assert_allclose(float(d2.sum()), 2.0 * n * lam, rtol=1e-4)
+
+
+def test_shortest_paths_retain_fraction_and_graph_helpers():
+    import pymde_b200 as pm
+    from pymde_b200.preprocess import graph as G
+    n = 300
+    g = Graph.from_edges(np.array([(i, (i + 1) % n) for i in range(n)]))
+    full = shortest_paths(g)
+    pm.seed(0)
+    a = shortest_paths(g, retain_fraction=0.25)
+    pm.seed(0)
+    b = shortest_paths(g, retain_fraction=0.25)
+    assert torch.equal(a.edges, b.edges) and torch.equal(a.distances, b.distances)  # seeded => reproducible
+    assert 0.2 * full.n_edges < a.n_edges < 0.3 * full.n_edges
+    # every retained pair carries the same distance as in the full graph
+    key = lambda e: (e[:, 0] * n + e[:, 1]).numpy()
+    pos = np.searchsorted(key(full.edges), key(a.edges))
+    np.testing.assert_array_equal(full.distances.numpy()[pos], a.distances.numpy())
+    # scale(): RMS of the distances becomes the natural length, structure untouched
+    sc = G.scale(full, 2.0)
+    np.testing.assert_allclose(float(sc.distances.pow(2).mean().sqrt()), 2.0, rtol=1e-5)
+    assert torch.equal(sc.edges, full.edges)
+    # breadth_first_order(): hop counts with inf for unreachable nodes, -9999 for "no predecessor"
+    h = Graph.from_edges(np.array([[0, 1], [1, 2], [3, 4]]), n_items=6)
+    lengths, pred = G.breadth_first_order(h.A, 0)
+    assert lengths.tolist() == [0.0, 1.0, 2.0, np.inf, np.inf, np.inf]
+    assert pred[1] == 0 and pred[2] == 1 and pred[0] == -9999 and pred[5] == -9999
+    assert pm.preprocess.generic.distances is pm.preprocess.distances
+    with pytest.raises(ValueError):
+        shortest_paths("not a graph")
