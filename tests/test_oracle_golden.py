@@ -135,3 +135,42 @@ def test_trajectory_f32_close_to_reference_f32(golden, key):
     np.testing.assert_allclose(st.average_distortions[0], ref[0], rtol=2e-6)
     final, _ = O.average_distortion(X, g[key + "/edges"], spec, False, np.float32)
     np.testing.assert_allclose(final, g[key + "/final_value"], rtol=1e-2)
+
+
+@pytest.mark.parametrize("name", sorted(__import__("tests.golden_cases", fromlist=["CASES"]).CASES))
+def test_closed_form_derivative_matches_central_differences(name):
+    """Independent of the reference fixtures: the oracle's closed-form f' is the derivative of its f
+    (float64 central differences, away from the kinks of the piecewise functions)."""
+    from tests.golden_cases import CASES
+    fa, sa, fr, sr = CASES[name]
+    rng = np.random.default_rng(abs(hash_name(name)))
+    p = 400
+    d = rng.uniform(0.15, 3.0, p)
+    if fr is not None:
+        par0 = rng.choice([-1.0, 1.0, 2.0], p)
+    elif fa >= O.L_ABSOLUTE:
+        par0 = rng.uniform(0.3, 2.5, p)  # deviations
+    else:
+        par0 = rng.uniform(0.5, 2.0, p)  # weights
+    par1 = rng.uniform(0.5, 2.0, p) if fa == O.L_WEIGHTED_QUADRATIC else None
+    spec = O.FnSpec(fa, par0, sa, fn_rep=fr, rep=sr, par1=par1)
+    h = 1e-6
+    f, fp = O.eval_function(spec, d)
+    fplus, _ = O.eval_function(spec, d + h)
+    fminus, _ = O.eval_function(spec, d - h)
+    num = (fplus - fminus) / (2 * h)
+    # skip points within 1e-3 of a kink (|d - delta|, Huber thresholds, fractional d = delta)
+    smooth = np.ones(p, dtype=bool)
+    if fa >= O.L_ABSOLUTE:
+        smooth &= np.abs(d - par0) > 1e-3
+        if fa == O.L_HUBER:
+            smooth &= np.abs(np.abs(d - par0) - sa[0]) > 1e-3
+    if fa == O.P_HUBER:
+        smooth &= np.abs(d - sa[0]) > 1e-3
+    assert smooth.sum() > p // 2
+    np.testing.assert_allclose(fp[smooth], num[smooth], rtol=2e-5, atol=1e-6)
+
+
+def hash_name(name):
+    import zlib
+    return zlib.crc32(name.encode())
