@@ -174,3 +174,30 @@ def test_closed_form_derivative_matches_central_differences(name):
 def hash_name(name):
     import zlib
     return zlib.crc32(name.encode())
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 5])
+@pytest.mark.parametrize("name", ["pen_pushpull_log1p_log", "loss_huber_0.7", "pen_quadratic", "loss_soft_fractional_10"])
+def test_gradient_of_average_distortion_matches_central_differences(name, m):
+    """dE/dX of the oracle (closed form through f') against float64 central differences of E."""
+    from tests.golden_cases import CASES
+    fa, sa, fr, sr = CASES[name]
+    rng = np.random.default_rng(hash_name(name) % 9973 + m)
+    n, p = 12, 40
+    e = rng.integers(0, n, (p, 2))
+    e = e[e[:, 0] != e[:, 1]]
+    p = len(e)
+    par0 = rng.choice([-1.0, 1.0, 2.0], p) if fr is not None else rng.uniform(0.5, 2.0, p)
+    spec = O.FnSpec(fa, par0, sa, fn_rep=fr, rep=sr)
+    X = rng.standard_normal((n, m)) * 1.5
+    v, g = O.average_distortion(X, e, spec, True)
+    num = np.zeros_like(X)
+    h = 1e-6
+    for i in range(n):
+        for c in range(m):
+            Xp, Xm = X.copy(), X.copy()
+            Xp[i, c] += h
+            Xm[i, c] -= h
+            num[i, c] = (O.average_distortion(Xp, e, spec, False)[0] - O.average_distortion(Xm, e, spec, False)[0]) / (2 * h)
+    np.testing.assert_allclose(g, num, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(g.sum(0), 0.0, atol=1e-12)  # translation invariance
