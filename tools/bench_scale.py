@@ -73,7 +73,7 @@ def main():
     b_alg = p_local * 12 + 2 * a.n * 2 * 4 + 8
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) \
         if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
-    # parity spot-check on a bounded sample of this rank's edges (C oracle), value only
+    # solver timing on the same layout
     solver = mde._solver(mde.constraint, 10, a.iters + 8)
     solver.begin(X0, 0.0); solver.run(3)
     if world > 1: td.barrier()
