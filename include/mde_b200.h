@@ -32,6 +32,7 @@ extern "C" {
 #define MDE_E_UNSUPPORTED (-2) /* combination not built (e.g. Standardized with m > 32) */
 #define MDE_E_NAN       (-3)  /* line search: function/gradient stayed NaN/Inf (lbfgs.py:70-80) */
 #define MDE_E_ALLOC     (-4)
+#define MDE_E_COMM      (-5)  /* multi-GPU: a peer never arrived at the all-reduce handshake (bounded spin) */
 
 /* distortion function ids -- pymde/functions/penalties.py, pymde/functions/losses.py */
 enum {
@@ -190,6 +191,16 @@ int mde_solver_stats(mde_solver_t* s, double* average_distortions_host, double* 
  * on `stream` (an NCCL all-reduce).  buf = [partial gradient (n*m) | loss hi | loss lo]. */
 typedef int (*mde_allreduce_fn)(void* user, float* buf, int64_t count, void* stream);
 int mde_solver_set_allreduce(mde_solver_t* s, mde_allreduce_fn fn, void* user);
+
+/* Peer-memory all-reduce (world_size > 1, one process per GPU on one NVLink node): the preferred path.
+ * Every rank exports the cudaIpc handle of its partial-gradient region (64 bytes), the ranks exchange the handles
+ * out of band (torch.distributed.all_gather in pymde_b200/dist.py), and mde_solver_comm_connect maps the peers'
+ * regions.  From then on each evaluation's all-reduce is done by the library's own kernels over NVLink
+ * (flag handshake + rank-ordered sums: bit-identical on every rank), graph-captured with the rest of the step;
+ * the host hook above is not used.  `handles` = world_size handles, `handle_stride` bytes apart, rank order. */
+#define MDE_IPC_HANDLE_BYTES 64
+int mde_solver_comm_export(mde_solver_t* s, void* handle_out, int64_t handle_bytes);
+int mde_solver_comm_connect(mde_solver_t* s, int rank, const void* handles, int64_t handle_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@
 #include <new>
 #include <utility>
 
-#include "mde_common.cuh"
+#include "mde_edges.cuh"
 
 namespace mde {
 unsigned long long g_launch_count = 0;
@@ -32,18 +32,6 @@ unsigned long long g_launch_count = 0;
 
 using namespace mde;
 
-struct mde_edges {
-  int64_t p = 0, n = 0, p_total = 0;
-  int32_t *src = nullptr, *dst = nullptr, *perm = nullptr;
-  float *par0 = nullptr, *par1 = nullptr;
-  double* loss_partials = nullptr;  // [kMaxLossBlocks]
-  FnDev fn;
-  int has_par1 = 0;
-  int tiled = 0;  // edge order grouped into L2-sized (src_tile, dst_tile) buckets
-  int64_t nbytes = 0;
-};
-
-static constexpr int kMaxLossBlocks = 148 * 16;
 static constexpr int kSmallThreads = 256;
 static constexpr int kRounds = 4;  // 32-edge rounds per warp iteration
 
@@ -62,34 +50,10 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ edges, const float*
   vals[k] = (int32_t)k;
 }
 
-// Second-level key for large graphs: (class, src_tile, dst_tile).  A stable sort on it after the
-// (class, src, dst) sort groups the edges into tile-pair buckets whose vertex rows (X and gradient of
-// both tiles) fit in the 126 MB L2, so the random gathers / reds of a bucket hit L2 instead of HBM.
-__global__ void tile_keys_kernel(const uint64_t* __restrict__ keys, int64_t p, int64_t tile_rows,
-                                 uint32_t* __restrict__ tkeys, int32_t* __restrict__ idx) {
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p) return;
-  const uint64_t key = keys[k];
-  const uint32_t cls = (uint32_t)(key >> 63);
-  const uint32_t s = (uint32_t)((key >> 32) & 0x7fffffffu), d = (uint32_t)(key & 0xffffffffu);
-  tkeys[k] = (cls << 16) | ((uint32_t)(s / tile_rows) << 8) | (uint32_t)(d / tile_rows);
-  idx[k] = (int32_t)k;
-}
-
-__global__ void gather_sorted_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
-                                     const int32_t* __restrict__ order, int64_t p, uint64_t* __restrict__ keys2,
-                                     int32_t* __restrict__ vals2) {
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p) return;
-  const int32_t o = order[k];
-  keys2[k] = keys[o];
-  vals2[k] = vals[o];
-}
-
 __global__ void unpack_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
                               const float* __restrict__ par0, const float* __restrict__ par1, int64_t p,
                               int32_t* __restrict__ src, int32_t* __restrict__ dst,
-                              float* __restrict__ p0, float* __restrict__ p1) {
+                              float* __restrict__ p0, float* __restrict__ p1, int32_t* __restrict__ perm) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p4 = (p + 3) & ~(int64_t)3;  // arrays are padded to a multiple of 4 edges
   if (k >= p4) return;
@@ -100,6 +64,7 @@ __global__ void unpack_kernel(const uint64_t* __restrict__ keys, const int32_t* 
   int32_t o = vals[kk];
   p0[k] = par0[o];
   if (par1) p1[k] = par1[o];
+  perm[k] = o;  // padded like the other arrays: the quad kernel loads it as int4 (MODE 2)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -668,10 +633,12 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
 
 // used by the solver: fused launch leaving per-block loss partials in e->loss_partials
 int distortion_fused(const mde_edges* e, const float* X, int m, float* grad, int* nblocks, cudaStream_t st) {
+  if (e->kind == 1) return tiled_launch(0, e, X, m, grad, nullptr, nblocks, nullptr, st);
   return launch_distortion<0>(e, X, m, grad, nullptr, nblocks, nullptr, st);
 }
 int distortion_fused_flag(const mde_edges* e, const float* X, int m, float* grad, int* nblocks,
                           const int* flag, cudaStream_t st) {
+  if (e->kind == 1) return tiled_launch(0, e, X, m, grad, nullptr, nblocks, flag, st);
   return launch_distortion<0>(e, X, m, grad, nullptr, nblocks, flag, st);
 }
 int64_t edges_p_total(const mde_edges* e) { return e->p_total; }
@@ -694,6 +661,7 @@ const char* mde_error_string(int code) {
     case MDE_E_UNSUPPORTED: return "mde: unsupported configuration";
     case MDE_E_NAN: return "mde: function or gradient evaluation returned NaN/Inf";
     case MDE_E_ALLOC: return "mde: allocation failed";
+    case MDE_E_COMM: return "mde: multi-GPU handshake timed out (a peer rank never arrived)";
   }
   return "mde: unknown error";
 }
@@ -702,6 +670,15 @@ int mde_edges_create(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t
                      const float* par0, const float* par1, const mde_fn_t* fn, int64_t p_total,
                      void* stream) {
   return mde_edges_create_ex(out, edges, p, n_items, par0, par1, fn, p_total, 2, stream);
+}
+
+// layout choice: MDE_B200_LAYOUT=soa forces the sorted-SoA layout (quad / strided kernels), =tiles insists on
+// the tile-record layout whenever it can be built; default: tiles for m <= 4 without a second parameter array
+static int layout_pref() {  // read at every create: A/B runs build both layouts in one process
+  const char* ev = getenv("MDE_B200_LAYOUT");
+  if (ev && !strcmp(ev, "soa")) return 1;
+  if (ev && !strcmp(ev, "tiles")) return 2;
+  return 0;
 }
 
 int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t n_items,
@@ -721,6 +698,13 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
   size_t tmp_bytes = 0;
   int rc = 0;
 #define TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
+  TRY(cudaMalloc(&e->loss_partials, sizeof(double) * kMaxLossBlocks));
+  if (embedding_dim >= 1 && embedding_dim <= 4 && !par1 && layout_pref() != 1) {
+    rc = tiled_build(e, edges, par0, fn, embedding_dim, st);
+    if (rc == 0) { *out = e; return 0; }
+    if (rc != MDE_E_UNSUPPORTED) goto fail;
+    rc = 0;  // not suited to tiles (very sparse / huge): sorted-SoA layout below
+  }
   TRY(cudaMalloc(&keys_in, sizeof(uint64_t) * p));
   TRY(cudaMalloc(&keys_out, sizeof(uint64_t) * p));
   TRY(cudaMalloc(&vals_in, sizeof(int32_t) * p));
@@ -728,8 +712,8 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
   TRY(cudaMalloc(&e->src, sizeof(int32_t) * (p + 4)));
   TRY(cudaMalloc(&e->dst, sizeof(int32_t) * (p + 4)));
   TRY(cudaMalloc(&e->par0, sizeof(float) * (p + 4)));
+  TRY(cudaMalloc(&e->perm, sizeof(int32_t) * (p + 4)));
   if (par1) TRY(cudaMalloc(&e->par1, sizeof(float) * (p + 4)));
-  TRY(cudaMalloc(&e->loss_partials, sizeof(double) * kMaxLossBlocks));
   e->nbytes = p * (4 + 4 + 4 + 4 + (par1 ? 4 : 0)) + 8 * kMaxLossBlocks;
   {
     int tb = 256;
@@ -740,47 +724,13 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
     TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p, 0, 64, st));
     TRY(cudaMalloc(&tmp, tmp_bytes));
     TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p, 0, 64, st));
-    // L2 tiling: 4 tiles (X and gradient rows of the src and dst tile) should stay within ~48 MB
-    {
-      const char* ev = getenv("MDE_B200_TILE_ROWS");
-      const int md = embedding_dim > 0 ? embedding_dim : 2;
-      // Measured on B200 (profiles/r01_ncu_summary.md section 2): at n = 1e7, p = 1e8 the kernel is bound by L2 sector
-      // operations (one random 32-byte gather + one random 32-byte red per edge), not by HBM misses, and
-      // the bucket order gains nothing (1.56 ms tiled vs 1.53 ms untiled).  Kept as an opt-in experiment:
-      // MDE_B200_TILE_ROWS=<rows> (e.g. 48 MB / (16 * m)).
-      (void)md;
-      int64_t tile_rows = ev ? atoll(ev) : 0;
-      if (tile_rows > 0 && n_items > tile_rows && (n_items + tile_rows - 1) / tile_rows <= 255) {
-        uint32_t *tk_in = nullptr, *tk_out = nullptr;
-        int32_t* ord_out = nullptr;
-        void* tmp2 = nullptr;
-        size_t tmp2_bytes = 0;
-        TRY(cudaMalloc(&tk_in, sizeof(uint32_t) * p));
-        TRY(cudaMalloc(&tk_out, sizeof(uint32_t) * p));
-        TRY(cudaMalloc(&ord_out, sizeof(int32_t) * p));
-        tile_keys_kernel<<<nb, tb, 0, st>>>(keys_out, p, tile_rows, tk_in, vals_in);
-        ++g_launch_count;
-        TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp2_bytes, tk_in, tk_out, vals_in, ord_out, (int)p, 0, 17, st));
-        TRY(cudaMalloc(&tmp2, tmp2_bytes));
-        TRY(cub::DeviceRadixSort::SortPairs(tmp2, tmp2_bytes, tk_in, tk_out, vals_in, ord_out, (int)p, 0, 17, st));
-        gather_sorted_kernel<<<nb, tb, 0, st>>>(keys_out, vals_out, ord_out, p, keys_in, vals_in);
-        ++g_launch_count;
-        TRY(cudaPeekAtLastError());
-        TRY(cudaStreamSynchronize(st));
-        std::swap(keys_in, keys_out);
-        std::swap(vals_in, vals_out);
-        cudaFree(tk_in); cudaFree(tk_out); cudaFree(ord_out); cudaFree(tmp2);
-        e->tiled = 1;
-      }
-    }
-    unpack_kernel<<<ceil_div_i64(p + 4, tb), tb, 0, st>>>(keys_out, vals_out, par0, par1, p, e->src, e->dst, e->par0, e->par1);
+    unpack_kernel<<<ceil_div_i64(p + 4, tb), tb, 0, st>>>(keys_out, vals_out, par0, par1, p, e->src, e->dst, e->par0,
+                                                         e->par1, e->perm);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());
     TRY(cudaStreamSynchronize(st));
   }
-  e->perm = vals_out;  // keep: original position of each sorted edge
-  vals_out = nullptr;
-  cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(tmp);
+  cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(vals_out); cudaFree(tmp);
   *out = e;
   return 0;
 fail:
@@ -794,6 +744,7 @@ int mde_edges_destroy(mde_edges_t* e) {
   if (!e) return 0;
   cudaFree(e->src); cudaFree(e->dst); cudaFree(e->perm); cudaFree(e->par0); cudaFree(e->par1);
   cudaFree(e->loss_partials);
+  tiled_free(e);
   delete e;
   return 0;
 }
@@ -806,7 +757,8 @@ int mde_distortion(const mde_edges_t* e, const float* X, int m, float* grad, dou
   if (!e || !X || m < 1) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int nb = 0, rc;
-  if (grad) rc = launch_distortion<0>(e, X, m, grad, nullptr, &nb, nullptr, st);
+  if (e->kind == 1) rc = tiled_launch(grad ? 0 : 1, e, X, m, grad, nullptr, &nb, nullptr, st);
+  else if (grad) rc = launch_distortion<0>(e, X, m, grad, nullptr, &nb, nullptr, st);
   else rc = launch_distortion<1>(e, X, m, nullptr, nullptr, &nb, nullptr, st);
   if (rc) return rc;
   if (loss_sum) {  // NULL: leave the per-block partials (kernel-only timing)
@@ -829,6 +781,7 @@ int mde_function_eval(const mde_fn_t* fn, const float* par0, int64_t par0_len, c
 int mde_scatter_external(const mde_edges_t* e, const float* X, int m, const float* g, float* grad,
                          void* stream) {
   if (!e || !X || !g || !grad || m < 1) return MDE_E_INVALID;
+  if (e->kind == 1) return tiled_launch(2, e, X, m, grad, g, nullptr, nullptr, (cudaStream_t)stream);
   return launch_distortion<2>(e, X, m, grad, g, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -836,6 +789,7 @@ int mde_edge_outputs(const mde_edges_t* e, const float* X, int m, float* distanc
                      void* stream) {
   if (!e || !X || m < 1) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->kind == 1) return tiled_edge_outputs(e, X, m, distances, distortions, st);
   int tb = 256, nb = ceil_div_i64(e->p, tb);
   edge_outputs_kernel<0><<<nb, tb, 0, st>>>(e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr,
                                             e->perm, e->p, m, X, distances, distortions, e->fn);

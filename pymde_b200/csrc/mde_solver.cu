@@ -21,6 +21,7 @@
 //    trial's loss.
 #include <cstddef>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 
 #include "mde_common.cuh"
@@ -661,6 +662,145 @@ pack_loss_kernel(const int* flag, const double* __restrict__ lpart, int nl, floa
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Multi-GPU: edge shards, X replicated, ONE all-reduce of [gradient | loss] per evaluation.
+// The all-reduce is done by OUR kernels over NVLink peer memory (cudaIpc-mapped buffers of the other ranks), not by
+// a host-side NCCL call: plain kernel nodes, so the sharded solve runs the same CUDA graph of gated steps as one
+// GPU, and a gated-off step costs nothing.  Every rank sums the peers' partial buffers in RANK ORDER, so all ranks
+// hold bit-identical gradients (the replicated Wolfe / L-BFGS decisions depend on it).
+//   small buffers (<= kOneShotBytes): one-shot -- every rank reads all W partial buffers and writes g;
+//   large buffers: two-shot -- rank r reduces chunk r in place (reduce-scatter), then everybody gathers the
+//   W reduced chunks (all-gather): 2 (W-1)/W of the buffer over NVLink instead of (W-1).
+// Handshake: monotonically increasing epochs in per-rank flag arrays (st.release.sys / ld.acquire.sys),
+// fa = "my partial buffer is complete", fb = "my chunk is reduced", fd = "I have finished reading the peers".
+// Spins are bounded: a peer that never arrives sets the solver's error word instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxWorld = 8;
+constexpr int kCommThreads = 512;
+constexpr int64_t kOneShotBytes = 4ll << 20;
+constexpr long long kSpinLimitCycles = 20000000000ll;  // ~10 s at 2 GHz
+
+struct Comm {
+  int rank, world;
+  float* buf[kMaxWorld];      // partial [gradient | hi lo] buffer of every rank (peer-mapped)
+  unsigned* fa[kMaxWorld];    // flag arrays of every rank: f?[q][r] is written by rank r, polled by rank q
+  unsigned* fb[kMaxWorld];
+  unsigned* fd[kMaxWorld];
+  unsigned* epoch;            // local: all-reduces completed so far
+  unsigned int* ticket;       // local last-block-done counter
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {  // never served from a stale L1 line
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// tell every rank "my epoch for this flag kind is `v`" (threads 0..W-1 of one block)
+__device__ __forceinline__ void comm_signal(unsigned* const* flags, const Comm& c, unsigned v) {
+  __threadfence_system();
+  if ((int)threadIdx.x < c.world) st_release_sys(flags[threadIdx.x] + c.rank, v);
+}
+// wait until every rank has signalled epoch >= v in MY flag array; all threads of the block call
+__device__ __forceinline__ void comm_wait(const unsigned* mine, const Comm& c, unsigned v, int* err) {
+  if ((int)threadIdx.x < c.world) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine + threadIdx.x) - v) < 0) {
+      if (clock64() - t0 > kSpinLimitCycles) { atomicExch(err, MDE_E_COMM); break; }
+    }
+  }
+  __syncthreads();
+}
+
+// before this rank overwrites its partial buffer: every peer must have finished reading it
+__device__ __forceinline__ void comm_wait_readers(const Comm& c, int* err) {
+  comm_wait(c.fd[c.rank], c, *reinterpret_cast<volatile unsigned*>(c.epoch), err);
+}
+
+__device__ __forceinline__ void comm_wait_readers_fwd(const Comm* c, int* err) { comm_wait_readers(*c, err); }
+
+// loss (hi, lo) pairs of all ranks summed in double, in rank order -> out[0..1]
+__device__ __forceinline__ void comm_reduce_tail(const Comm& c, int64_t npad, float* out) {
+  double sum = 0.0;
+  for (int q = 0; q < c.world; ++q) {
+    const volatile float* t = c.buf[q] + npad;
+    sum += (double)t[0] + (double)t[1];
+  }
+  const float hi = (float)sum;
+  out[0] = hi;
+  out[1] = (float)(sum - (double)hi);
+}
+
+// One-shot: g[i] = sum_q buf_q[i] (rank order) for i < npad, tail summed in double.  MODE 0 = one-shot,
+// 1 = reduce-scatter phase (chunk `rank` reduced in place), 2 = all-gather phase.
+template <int PHASE>
+__global__ void __launch_bounds__(kCommThreads)
+allreduce_kernel(const int* __restrict__ flag, Comm c, float* __restrict__ g, int64_t npad, int* __restrict__ err) {
+  if (off(flag)) return;
+  const unsigned ep = *reinterpret_cast<volatile unsigned*>(c.epoch) + 1u;
+  unsigned* const* sig = (PHASE == 2) ? c.fb : c.fa;
+  if (blockIdx.x == 0) comm_signal(sig, c, ep);
+  comm_wait(sig[c.rank], c, ep, err);
+  const int64_t n4 = npad >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (PHASE == 0) {
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 acc = ld_peer_f4(c.buf[0] + 4 * i);
+      for (int q = 1; q < c.world; ++q) {
+        const float4 v = ld_peer_f4(c.buf[q] + 4 * i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(g)[i] = acc;
+    }
+    if (tid == 0) comm_reduce_tail(c, npad, g + npad);
+  } else {
+    // chunk q = [q * cs, min((q + 1) * cs, n4)) in float4 units
+    const int64_t cs = (n4 + c.world - 1) / c.world;
+    if (PHASE == 1) {
+      const int64_t lo = (int64_t)c.rank * cs, hi = (lo + cs < n4) ? lo + cs : n4;
+      for (int64_t i = lo + tid; i < hi; i += stride) {
+        float4 acc = ld_peer_f4(c.buf[0] + 4 * i);
+        for (int q = 1; q < c.world; ++q) {
+          const float4 v = ld_peer_f4(c.buf[q] + 4 * i);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(c.buf[c.rank])[i] = acc;
+      }
+      if (tid == 0) comm_reduce_tail(c, npad, g + npad);
+    } else {
+      for (int64_t i = tid; i < n4; i += stride) {
+        int q = (int)(i / cs);
+        reinterpret_cast<float4*>(g)[i] = ld_peer_f4(c.buf[q] + 4 * i);
+      }
+    }
+  }
+  if (PHASE != 1) {
+    // the last block to finish tells the peers "I am done reading your buffers" and completes the epoch
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(c.ticket, 1u);
+      s_last = (t == gridDim.x - 1u) ? 1 : 0;
+      if (s_last) *c.ticket = 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+      comm_signal(c.fd, c, ep);
+      if (threadIdx.x == 0) *c.epoch = ep;
+    }
+  }
+}
+
 // T5: partial g.d, g.g, |g|_1
 __global__ void __launch_bounds__(kVecThreads)
 grad_dots_kernel(const int* flag, const float* __restrict__ g, const float* __restrict__ d, int64_t npad,
@@ -893,6 +1033,7 @@ __device__ void step_end_body(SolverState* __restrict__ S, const double* __restr
   if (ph == PH_FRESH) fresh_finish_body(S, lpart, nl, tail, dpart, nd, p_total);
   else if (ph != PH_MAT) ls_update_body(S, lpart, nl, tail, dpart, nd, p_total, 0);
   if (threadIdx.x != 0) return;
+  if (S->error == MDE_E_COMM) S->active = 0;  // a peer never arrived: stop instead of timing out once per step
   int next = ph;
   bool end_of_iteration = false;
   if (ph == PH_FRESH) next = PH_DIR;
@@ -924,9 +1065,11 @@ __global__ void resume_kernel(SolverState* __restrict__ S, int limit) {
 // is applied on the fly like trial_axpy_kernel.
 __global__ void __launch_bounds__(kVecThreads)
 step_axpy_kernel(SolverState* __restrict__ S, const float* __restrict__ xinit, const float* __restrict__ d,
-                 float* __restrict__ X, int64_t npad, int64_t nvalid, int center_m, float* __restrict__ gz) {
+                 float* __restrict__ X, int64_t npad, int64_t nvalid, int center_m, float* __restrict__ gz,
+                 const Comm* __restrict__ comm) {
   if (off(&S->active)) return;
   const bool mat = S->g_mat != 0;
+  if (comm != nullptr && !mat) comm_wait_readers_fwd(comm, &S->error);  // gz is the peer-visible partial buffer
   const bool move = S->g_proj != 0;  // every phase but PH_FRESH
   if (move && !mat && off(&S->ls_active)) return;
   const float t = mat ? (float)S->ls.t_accept : (float)S->ls.t;
@@ -1006,6 +1149,14 @@ struct mde_solver {
   int host_evals = 0;                // func_evals already accounted in the launch counter (mode 1)
   mde_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  // peer-memory all-reduce (world_size > 1): one cudaMalloc region [partial buffer | flags | epoch | ticket],
+  // exported with cudaIpc, the peers' regions mapped by mde_solver_comm_connect
+  void* comm_region = nullptr;
+  int64_t comm_bytes = 0, comm_flags_off = 0;
+  Comm comm{};
+  Comm* comm_dev = nullptr;
+  int comm_connected = 0;
+  void* peer_base[kMaxWorld] = {nullptr};
   int64_t* anchors = nullptr;
   float* anchor_values = nullptr;
   // mode 1: one CUDA graph per iteration with an IF node (fresh evaluation) and a WHILE node (trials)
@@ -1066,9 +1217,9 @@ Tail make_tail(mde_solver* s, int mode) {
 }
 
 int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cudaStream_t st) {
-  // mode 2 on several GPUs: scatter into the staging buffer, all-reduce it (unconditionally -- the host does
-  // not know the phase), then copy it into g under the evaluation gate
-  const bool staged = (s->opts.mode == 2 && s->opts.world_size > 1);
+  // several GPUs: scatter into this rank's partial buffer (peer-visible), then all-reduce into g
+  const bool multi = s->opts.world_size > 1;
+  const bool staged = multi && s->opts.mode == 2;  // (the peer-memory path exists in mode 2 only)
   float* target = staged ? s->gpart : s->g;
   if (zero_g) {
     const int64_t n4 = (s->npad + 4) >> 2;  // gradient + (hi, lo) tail
@@ -1077,16 +1228,33 @@ int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cud
   }
   int rc = distortion_fused_flag(s->edges, s->X, s->m, target, &s->nl, flag, st);
   if (rc) return rc;
-  if (s->opts.world_size > 1) {
+  if (multi) {
     pack_loss_kernel<<<1, 256, 0, st>>>(flag, loss_partials_ptr(s->edges), s->nl, target + s->npad);
     MDE_LAUNCH_CHECK();
-    if (!s->allreduce) return MDE_E_INVALID;
-    rc = s->allreduce(s->allreduce_user, target, s->npad + 4, (void*)st);
-    if (rc) return rc;
-    if (staged) {
-      const int64_t n4 = (s->npad + 4) >> 2;
-      gated_copy_kernel<<<vec_blocks(n4), kVecThreads, 0, st>>>(flag, s->gpart, s->g, n4);
-      MDE_LAUNCH_CHECK();
+    if (s->comm_connected) {
+      const int64_t n4 = s->npad >> 2;
+      int nb = (int)((n4 + kCommThreads - 1) / kCommThreads);
+      if (nb > kNumSMs * 2) nb = kNumSMs * 2;
+      if (nb < 1) nb = 1;
+      if ((s->npad + 4) * (int64_t)sizeof(float) <= kOneShotBytes) {
+        allreduce_kernel<0><<<nb, kCommThreads, 0, st>>>(flag, s->comm, s->g, s->npad, &s->S->error);
+        MDE_LAUNCH_CHECK();
+      } else {
+        allreduce_kernel<1><<<nb, kCommThreads, 0, st>>>(flag, s->comm, s->g, s->npad, &s->S->error);
+        MDE_LAUNCH_CHECK();
+        allreduce_kernel<2><<<nb, kCommThreads, 0, st>>>(flag, s->comm, s->g, s->npad, &s->S->error);
+        MDE_LAUNCH_CHECK();
+      }
+    } else {
+      // host hook (an NCCL all-reduce enqueued by the caller between two kernels): not graph-capturable
+      if (!s->allreduce) return MDE_E_INVALID;
+      rc = s->allreduce(s->allreduce_user, target, s->npad + 4, (void*)st);
+      if (rc) return rc;
+      if (staged) {
+        const int64_t n4 = (s->npad + 4) >> 2;
+        gated_copy_kernel<<<vec_blocks(n4), kVecThreads, 0, st>>>(flag, s->gpart, s->g, n4);
+        MDE_LAUNCH_CHECK();
+      }
     }
   }
   const int* act = flag;
@@ -1175,7 +1343,8 @@ int enqueue_step(mde_solver* s, cudaStream_t st) {
   int rc = enqueue_direction(s, st, &S->g_dir);
   if (rc) return rc;
   step_axpy_kernel<<<s->nvb, kVecThreads, 0, st>>>(S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m,
-                                                   s->opts.world_size > 1 ? s->gpart : s->g);
+                                                   s->opts.world_size > 1 ? s->gpart : s->g,
+                                                   s->comm_connected ? s->comm_dev : nullptr);
   MDE_LAUNCH_CHECK();
   switch (s->opts.constraint) {  // retraction of the moved iterate (project_callback, lbfgs.py:368-372)
     case MDE_CONSTRAINT_CENTERED:
@@ -1325,7 +1494,16 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   TRY(cudaMallocHost(&s->status_host, kStatusInts * sizeof(int)));
   TRY(cudaMalloc(&s->X, vb)); TRY(cudaMalloc(&s->xinit, vb)); TRY(cudaMalloc(&s->d, vb));
   TRY(cudaMalloc(&s->g, vb)); TRY(cudaMalloc(&s->gprev, vb));
-  if (opts->mode == 2 && opts->world_size > 1) { TRY(cudaMalloc(&s->gpart, vb)); TRY(cudaMemsetAsync(s->gpart, 0, vb, st)); }
+  if (opts->world_size > 1) {
+    if (opts->world_size > kMaxWorld) { rc = MDE_E_UNSUPPORTED; goto fail; }
+    // [partial buffer (vb bytes, 256-aligned) | fa[W] fb[W] fd[W] (64 B apart) | epoch | ticket]
+    s->comm_flags_off = (vb + 255) / 256 * 256;
+    s->comm_bytes = s->comm_flags_off + 64 * (3 * kMaxWorld + 2);
+    TRY(cudaMalloc(&s->comm_region, s->comm_bytes));
+    TRY(cudaMemsetAsync(s->comm_region, 0, s->comm_bytes, st));
+    TRY(cudaMalloc(&s->comm_dev, sizeof(Comm)));
+    s->gpart = reinterpret_cast<float*>(s->comm_region);
+  }
   TRY(cudaMalloc(&s->Sb, (int64_t)(opts->memory_size + 1) * s->npad * sizeof(float)));
   TRY(cudaMalloc(&s->Yb, (int64_t)(opts->memory_size + 1) * s->npad * sizeof(float)));
   TRY(cudaMalloc(&s->dpart, sizeof(double) * (int64_t)kVecBlocks * kDotsPerSlice * kMaxSlices));
@@ -1349,7 +1527,7 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   if (opts->constraint == MDE_CONSTRAINT_CENTERED && (m == 1 || m == 2 || m == 4)) s->center_m = m;
   { const char* ev = getenv("MDE_B200_FUSE"); if (ev && ev[0] == '0') s->fuse = 0; }
   if (opts->mode == 2) s->fuse = 1;  // the phase machine lives in the fused epilogues
-  if (opts->mode == 2 && opts->world_size == 1) {  // several GPUs: steps are stream launches (NCCL hook between)
+  if (opts->mode == 2 && opts->world_size == 1) {  // several GPUs: graphs are built by mde_solver_comm_connect
     s->nl = 0;
     TRY(cudaStreamSynchronize(st));
     rc = build_step_graph(s, 1, &s->step_graph, &s->step_exec);
@@ -1384,7 +1562,9 @@ fail:
 int mde_solver_destroy(mde_solver_t* s) {
   if (!s) return 0;
   cudaFree(s->S); cudaFreeHost(s->status_host);
-  cudaFree(s->X); cudaFree(s->xinit); cudaFree(s->d); cudaFree(s->g); cudaFree(s->gprev); cudaFree(s->gpart);
+  cudaFree(s->X); cudaFree(s->xinit); cudaFree(s->d); cudaFree(s->g); cudaFree(s->gprev);
+  for (int q = 0; q < kMaxWorld; ++q) if (s->peer_base[q]) cudaIpcCloseMemHandle(s->peer_base[q]);
+  cudaFree(s->comm_region); cudaFree(s->comm_dev);
   cudaFree(s->Sb); cudaFree(s->Yb); cudaFree(s->dpart); cudaFree(s->stats); cudaFree(s->projws);
   cudaFree(s->anchors); cudaFree(s->anchor_values);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -1404,6 +1584,63 @@ int mde_solver_destroy(mde_solver_t* s) {
 int mde_solver_set_allreduce(mde_solver_t* s, mde_allreduce_fn fn, void* user) {
   if (!s) return MDE_E_INVALID;
   s->allreduce = fn; s->allreduce_user = user;
+  return 0;
+}
+
+int mde_solver_comm_export(mde_solver_t* s, void* handle_out, int64_t handle_bytes) {
+  if (!s || !handle_out || !s->comm_region || handle_bytes < (int64_t)sizeof(cudaIpcMemHandle_t)) return MDE_E_INVALID;
+  cudaIpcMemHandle_t h;
+  MDE_CUDA_TRY(cudaIpcGetMemHandle(&h, s->comm_region));
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int mde_solver_comm_connect(mde_solver_t* s, int rank, const void* handles, int64_t handle_stride, void* stream) {
+  if (!s || !handles || !s->comm_region || rank < 0 || rank >= s->opts.world_size ||
+      handle_stride < (int64_t)sizeof(cudaIpcMemHandle_t))
+    return MDE_E_INVALID;
+  if (s->comm_connected) return MDE_E_INVALID;
+  if (s->opts.mode != 2) return MDE_E_UNSUPPORTED;  // host-stepped modes keep the host hook
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = s->opts.world_size;
+  Comm c{};
+  c.rank = rank; c.world = W;
+  for (int q = 0; q < W; ++q) {
+    char* base;
+    if (q == rank) base = reinterpret_cast<char*>(s->comm_region);
+    else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, reinterpret_cast<const char*>(handles) + (int64_t)q * handle_stride, sizeof(h));
+      void* ptr = nullptr;
+      MDE_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      s->peer_base[q] = ptr;
+      base = reinterpret_cast<char*>(ptr);
+    }
+    char* fl = base + s->comm_flags_off;
+    c.buf[q] = reinterpret_cast<float*>(base);
+    c.fa[q] = reinterpret_cast<unsigned*>(fl);
+    c.fb[q] = reinterpret_cast<unsigned*>(fl + 64 * kMaxWorld);
+    c.fd[q] = reinterpret_cast<unsigned*>(fl + 64 * 2 * kMaxWorld);
+  }
+  {
+    char* fl = reinterpret_cast<char*>(s->comm_region) + s->comm_flags_off;
+    c.epoch = reinterpret_cast<unsigned*>(fl + 64 * 3 * kMaxWorld);
+    c.ticket = reinterpret_cast<unsigned*>(fl + 64 * (3 * kMaxWorld + 1));
+  }
+  s->comm = c;
+  MDE_CUDA_TRY(cudaMemcpyAsync(s->comm_dev, &s->comm, sizeof(Comm), cudaMemcpyHostToDevice, st));
+  MDE_CUDA_TRY(cudaStreamSynchronize(st));
+  s->comm_connected = 1;
+  if (s->opts.mode == 2) {  // the sharded solve runs the same flat step graphs as one GPU
+    s->nl = 0;
+    int rc = build_step_graph(s, 1, &s->step_graph, &s->step_exec);
+    if (rc) return rc;
+    { const char* ev = getenv("MDE_B200_STEPS"); if (ev) s->steps_per_graph = atoi(ev); }
+    if (s->steps_per_graph < 1) s->steps_per_graph = 1;
+    if (s->steps_per_graph > 64) s->steps_per_graph = 64;
+    rc = build_step_graph(s, s->steps_per_graph, &s->steps_graph, &s->steps_exec);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -1452,8 +1689,8 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
       if (remaining < 1) remaining = 1;
       long long steps = 0;
       const int spg = s->steps_per_graph;
-      if (s->opts.world_size > 1) {
-        // every rank enqueues the same number of steps (same `remaining`: the replicated state machines agree)
+      if (s->opts.world_size > 1 && !s->steps_exec) {
+        // host-hook all-reduce: stream-launched steps; every rank enqueues the same number of steps (same `remaining`: the replicated state machines agree)
         int n_steps = remaining + remaining / 8 + (round > 0 ? 1 : 0);
         if (n_steps > 64) n_steps = 64;
         for (int b = 0; b < n_steps; ++b) { if ((rc = enqueue_step(s, st))) return rc; }

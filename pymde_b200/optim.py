@@ -52,7 +52,8 @@ DEFAULT_MODE = int(os.environ.get("PYMDE_B200_SOLVER_MODE", "2"))
 class DeviceSolver(object):
     """Owner of one `mde_solver_t`."""
 
-    def __init__(self, layout, n, m, constraint, memory_size, max_iter, world_size=1, allreduce=None, mode=None):
+    def __init__(self, layout, n, m, constraint, memory_size, max_iter, world_size=1, allreduce=None, mode=None,
+                 exchange=None, rank=0):
         lib = _lib.load()
         self.lib = lib
         self.layout = layout  # keep the edge layout alive
@@ -82,7 +83,19 @@ class DeviceSolver(object):
         self.handle = handle
         self.max_iter = opts.max_iter
         self._cb = None
-        if allreduce is not None:
+        self.peer_memory = False
+        if int(world_size) > 1 and exchange is not None and opts.mode == 2:
+            # peer-memory all-reduce: export this rank's cudaIpc handle, gather everybody's, map the peers
+            # (pymde_b200/dist.py::exchange_handles); the solve then runs graph-captured like on one GPU
+            mine = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.mde_solver_comm_export(self.handle, mine, _lib.IPC_HANDLE_BYTES))
+                handles = exchange(bytes(mine))  # world_size * 64 bytes, rank order
+                buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+                _lib.check(lib.mde_solver_comm_connect(self.handle, int(rank), buf, _lib.IPC_HANDLE_BYTES,
+                                                       util.stream_ptr(self.device)))
+            self.peer_memory = True
+        elif allreduce is not None:
             self._cb = _lib.ALLREDUCE_FN(allreduce)
             _lib.check(lib.mde_solver_set_allreduce(self.handle, self._cb, None))
 

@@ -60,6 +60,7 @@ class EdgeLayout(object):
         self.handle = handle
         self.loss = torch.zeros(1, dtype=torch.float64, device=device)
         self.p_total = int(self.p if p_total is None else p_total)
+        self.dist = None  # set by MDE._layout() for an edge shard: evaluations are summed across ranks
 
     def close(self):
         if getattr(self, "handle", None):
@@ -81,6 +82,9 @@ class EdgeLayout(object):
             _lib.check(self.lib.mde_distortion(self.handle, X.data_ptr(), m,
                                                None if grad is None else grad.data_ptr(),
                                                self.loss.data_ptr(), util.stream_ptr(self.device)))
+        if self.dist is not None:
+            from . import dist as pdist
+            pdist.allreduce_evaluation(self.loss, grad, self.dist.get("group"))
         value = (self.loss[0] / self.p_total).to(torch.float32)
         return value, grad
 
@@ -100,6 +104,9 @@ class EdgeLayout(object):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mde_scatter_external(self.handle, X.data_ptr(), X.shape[1], g.data_ptr(),
                                                      grad.data_ptr(), util.stream_ptr(self.device)))
+        if self.dist is not None:
+            import torch.distributed as tdist
+            tdist.all_reduce(grad, op=tdist.ReduceOp.SUM, group=self.dist.get("group"))
         return grad
 
 
@@ -130,17 +137,30 @@ class _ExternalAverageDistortion(torch.autograd.Function):
     def forward(ctx, X, layout, f):
         Xd = X.detach()
         norms, _ = layout.outputs(Xd, distances=True)
+
+        def mean(values):  # global mean: an edge shard divides by the global edge count and sums across ranks
+            if layout.dist is None:
+                return values.mean()
+            return values.sum() / layout.p_total
+
+        def reduced(value):
+            if layout.dist is not None:
+                import torch.distributed as tdist
+                value = value.clone()
+                tdist.all_reduce(value, op=tdist.ReduceOp.SUM, group=layout.dist.get("group"))
+            return value
+
         if X.requires_grad:
             with torch.enable_grad():
                 norms.requires_grad_(True)
-                distortion = f(norms).mean()
+                distortion = mean(f(norms))
                 distortion.backward()
                 norms.requires_grad_(False)
             g = norms.grad / norms
             g[~torch.isfinite(g)] = 1.0
             ctx.save_for_backward(layout.scatter_external(Xd, g.contiguous()))
-            return distortion.detach()
-        return f(norms).mean()
+            return reduced(distortion.detach())
+        return reduced(mean(f(norms)))
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -244,6 +264,7 @@ class MDE(torch.nn.Module):
             p_total = None if self.__dict__["_dist"] is None else self.__dict__["_dist"]["p_total"]
             lay = EdgeLayout(self.edges, int(self.n_items), table, par0, par1, self.device, p_total=p_total,
                              embedding_dim=int(self.embedding_dim))
+            lay.dist = self.__dict__["_dist"]
             self.__dict__["_edge_layout"] = lay
         return lay
 
@@ -256,7 +277,7 @@ class MDE(torch.nn.Module):
         if isinstance(constraint, constraints._Standardized) and int(self.embedding_dim) > 32:
             return False
         m = int(self.embedding_dim)
-        if m > 512 or (m % 4 == 0 and m > 1024):
+        if (m % 4 == 0 and m > 1024) or (m % 4 != 0 and m > 512):  # mirrors launch_distortion (mde_edges.cu)
             return False
         return 1 <= int(memory_size) <= 32
 
@@ -273,7 +294,9 @@ class MDE(torch.nn.Module):
             solver = optim.DeviceSolver(self._layout(), int(self.n_items), int(self.embedding_dim), constraint,
                                         memory_size, capacity,
                                         world_size=1 if dist is None else dist["world_size"],
-                                        allreduce=None if dist is None else dist["allreduce"])
+                                        allreduce=None if dist is None else dist.get("allreduce"),
+                                        exchange=None if dist is None else dist.get("exchange"),
+                                        rank=0 if dist is None else dist["rank"])
             cur = (key, solver)
             self.__dict__["_device_solver"] = cur
         return cur[1]
