@@ -307,8 +307,11 @@ def kernel_roofline(mde, X0d, m, p_local, n, torch, dev, lib, _lib, cold, profil
     b_alg = p_local * 12 + 2 * n * m * 4 + 8
     achieved = b_alg / (k_ms * 1e-3) / 1e9
     prof = load_profile(profile_key)
-    return {"bound": "hbm", "kernel": "distortion_tile_kernel<m=2, fused, LOG1P|LOG, fast-math> (tile-record layout)"
-            if os.environ.get("MDE_B200_LAYOUT") != "soa" else "distortion_quad_kernel<m=2, fused, LOG1P|LOG, fast-math>",
+    kind = int(lib.mde_edges_kind(lay.handle))
+    kernel = {0: "distortion_quad_kernel<m=2, fused, LOG1P|LOG, fast-math> (sorted-SoA layout)",
+              1: "distortion_tile_kernel<m=2, fused, LOG1P|LOG, fast-math> (tile-record layout, push)",
+              2: "distortion_pull_kernel<m=2, fused, LOG1P|LOG, fast-math> (pull-record layout)"}.get(kind, "?")
+    return {"bound": "hbm", "kernel": kernel,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None if prof is None else prof.get("dram_bytes"),
             "traffic_source": None if prof is None else prof.get("source"),

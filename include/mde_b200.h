@@ -90,14 +90,18 @@ uint64_t mde_launch_count(void);
 int mde_edges_create(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t n_items,
                      const float* par0, const float* par1 /* nullable */, const mde_fn_t* fn,
                      int64_t p_total, void* stream);
-/* Same, with the embedding dimension as a hint: graphs whose vertex rows exceed the L2 get their
- * edges grouped into (src_tile, dst_tile) buckets sized so that X and gradient rows of both tiles
- * stay L2-resident (tile = 48 MB / (16 * embedding_dim) rows). */
+/* Same, with the embedding dimension: for embedding_dim <= 4 dense graphs (>= 64 edges per item) get the
+ * tile-resident layout (pymde_b200/csrc/mde_pull.cu: vertex tiles of X live in shared memory, the edge records are
+ * streamed by TMA); everything else keeps the sorted-SoA layout. */
 int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t n_items,
                         const float* par0, const float* par1 /* nullable */, const mde_fn_t* fn,
                         int64_t p_total, int embedding_dim, void* stream);
 int mde_edges_destroy(mde_edges_t* e);
 int64_t mde_edges_count(const mde_edges_t* e);
+/* which layout / kernel family the library chose: 0 = sorted SoA (quad / strided / wide kernels), 1 = tile records
+ * (push kernel, shared-memory dst tile), 2 = pull records (directed entries, no shared-memory atomics).
+ * MDE_B200_LAYOUT=soa|tiles|pull overrides the choice (A/B measurements). */
+int mde_edges_kind(const mde_edges_t* e);
 /* bytes of device memory held by the layout */
 int64_t mde_edges_nbytes(const mde_edges_t* e);
 

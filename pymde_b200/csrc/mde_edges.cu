@@ -633,11 +633,13 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
 
 // used by the solver: fused launch leaving per-block loss partials in e->loss_partials
 int distortion_fused(const mde_edges* e, const float* X, int m, float* grad, int* nblocks, cudaStream_t st) {
+  if (e->kind == 2) return pull_launch(0, e, X, m, grad, nullptr, nblocks, nullptr, st);
   if (e->kind == 1) return tiled_launch(0, e, X, m, grad, nullptr, nblocks, nullptr, st);
   return launch_distortion<0>(e, X, m, grad, nullptr, nblocks, nullptr, st);
 }
 int distortion_fused_flag(const mde_edges* e, const float* X, int m, float* grad, int* nblocks,
                           const int* flag, cudaStream_t st) {
+  if (e->kind == 2) return pull_launch(0, e, X, m, grad, nullptr, nblocks, flag, st);
   if (e->kind == 1) return tiled_launch(0, e, X, m, grad, nullptr, nblocks, flag, st);
   return launch_distortion<0>(e, X, m, grad, nullptr, nblocks, flag, st);
 }
@@ -678,6 +680,7 @@ static int layout_pref() {  // read at every create: A/B runs build both layouts
   const char* ev = getenv("MDE_B200_LAYOUT");
   if (ev && !strcmp(ev, "soa")) return 1;
   if (ev && !strcmp(ev, "tiles")) return 2;
+  if (ev && !strcmp(ev, "pull")) return 3;
   return 0;
 }
 
@@ -696,13 +699,28 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
   int32_t *vals_in = nullptr, *vals_out = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
-  int rc = 0;
+  int rc = 0, pref = 0;
+  bool dense = false;
 #define TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
   TRY(cudaMalloc(&e->loss_partials, sizeof(double) * kMaxLossBlocks));
-  if (embedding_dim >= 1 && embedding_dim <= 4 && !par1 && layout_pref() != 1) {
-    rc = tiled_build(e, edges, par0, fn, embedding_dim, st);
-    if (rc == 0) { *out = e; return 0; }
-    if (rc != MDE_E_UNSUPPORTED) goto fail;
+  // Layout choice (measured on B200, profiles/r02_kernels.md): the SM's L1 -> L2 request path (~1 sector request per
+  // cycle) bounds the gather / scatter; the tile kernels trade requests for instructions (pull: every edge is
+  // evaluated from both ends) and win once an owner's run inside a tile is long, i.e. on dense graphs
+  // (C3: 447 edges per node, 2.0x faster); on sparse ones (C2: 22, C5: 10) the sorted-SoA quad kernel is as fast or
+  // faster, and needs half the layout memory.
+  dense = (p / n_items) >= 64;
+  pref = layout_pref();
+  if (embedding_dim >= 1 && embedding_dim <= 4 && !par1 && pref != 1 && (pref != 0 || dense)) {
+    if (layout_pref() != 2) {  // pull records
+      rc = pull_build(e, edges, par0, fn, embedding_dim, st);
+      if (rc == 0) { *out = e; return 0; }
+      if (rc != MDE_E_UNSUPPORTED) goto fail;
+    }
+    if (layout_pref() != 3) {
+      rc = tiled_build(e, edges, par0, fn, embedding_dim, st);
+      if (rc == 0) { *out = e; return 0; }
+      if (rc != MDE_E_UNSUPPORTED) goto fail;
+    }
     rc = 0;  // not suited to tiles (very sparse / huge): sorted-SoA layout below
   }
   TRY(cudaMalloc(&keys_in, sizeof(uint64_t) * p));
@@ -745,11 +763,13 @@ int mde_edges_destroy(mde_edges_t* e) {
   cudaFree(e->src); cudaFree(e->dst); cudaFree(e->perm); cudaFree(e->par0); cudaFree(e->par1);
   cudaFree(e->loss_partials);
   tiled_free(e);
+  pull_free(e);
   delete e;
   return 0;
 }
 
 int64_t mde_edges_count(const mde_edges_t* e) { return e ? e->p : 0; }
+int mde_edges_kind(const mde_edges_t* e) { return e ? e->kind : -1; }
 int64_t mde_edges_nbytes(const mde_edges_t* e) { return e ? e->nbytes : 0; }
 
 int mde_distortion(const mde_edges_t* e, const float* X, int m, float* grad, double* loss_sum,
@@ -757,7 +777,8 @@ int mde_distortion(const mde_edges_t* e, const float* X, int m, float* grad, dou
   if (!e || !X || m < 1) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int nb = 0, rc;
-  if (e->kind == 1) rc = tiled_launch(grad ? 0 : 1, e, X, m, grad, nullptr, &nb, nullptr, st);
+  if (e->kind == 2) rc = pull_launch(grad ? 0 : 1, e, X, m, grad, nullptr, &nb, nullptr, st);
+  else if (e->kind == 1) rc = tiled_launch(grad ? 0 : 1, e, X, m, grad, nullptr, &nb, nullptr, st);
   else if (grad) rc = launch_distortion<0>(e, X, m, grad, nullptr, &nb, nullptr, st);
   else rc = launch_distortion<1>(e, X, m, nullptr, nullptr, &nb, nullptr, st);
   if (rc) return rc;
@@ -781,6 +802,7 @@ int mde_function_eval(const mde_fn_t* fn, const float* par0, int64_t par0_len, c
 int mde_scatter_external(const mde_edges_t* e, const float* X, int m, const float* g, float* grad,
                          void* stream) {
   if (!e || !X || !g || !grad || m < 1) return MDE_E_INVALID;
+  if (e->kind == 2) return pull_launch(2, e, X, m, grad, g, nullptr, nullptr, (cudaStream_t)stream);
   if (e->kind == 1) return tiled_launch(2, e, X, m, grad, g, nullptr, nullptr, (cudaStream_t)stream);
   return launch_distortion<2>(e, X, m, grad, g, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -789,6 +811,7 @@ int mde_edge_outputs(const mde_edges_t* e, const float* X, int m, float* distanc
                      void* stream) {
   if (!e || !X || m < 1) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->kind == 2) return pull_edge_outputs(e, X, m, distances, distortions, st);
   if (e->kind == 1) return tiled_edge_outputs(e, X, m, distances, distortions, st);
   int tb = 256, nb = ceil_div_i64(e->p, tb);
   edge_outputs_kernel<0><<<nb, tb, 0, st>>>(e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr,

@@ -14,6 +14,11 @@
 //                               int32 src[128] | int32 dst[128] | fp32 par0[128]        (pad: dst = -1)
 //                           so a warp fetches it with a single cp.async.bulk (TMA) into its shared-memory slot.
 //                           perm[nwt * 128] holds the caller position of every slot (-1 for pads).
+//
+//  kind 2  "pull records"   m <= 4.  Same buckets, but every edge is stored as two DIRECTED entries (owner,
+//                           neighbour) and a bucket is (owner super-tile, neighbour tile, class); records are
+//                           1040 bytes: fp32 w[128] | u16 owner offset[128] | u16 neighbour offset[128] | header
+//                           (mde_pull.cu).  No shared-memory atomics, one global red per owner run.
 #pragma once
 #include "mde_common.cuh"
 
@@ -41,6 +46,8 @@ struct mde_edges {
   int ncta = 0;                 // persistent grid of the tile kernel
   int32_t* cta_wt0 = nullptr;   // [ncta + 1] warp-tile range of CTA c
   int32_t* cta_bkt0 = nullptr;  // [ncta]     bucket holding cta_wt0[c]
+  // ---- kind 2 (pull records, mde_pull.cu): same bucket / CTA tables, 1040-byte records of DIRECTED entries ----
+  int32_t* wt_tile = nullptr;   // [nwt] neighbour tile of every warp-tile (per-edge outputs)
 };
 
 namespace mde {
@@ -59,5 +66,14 @@ int tiled_launch(int mode, const mde_edges* e, const float* X, int m, float* gra
                  int* nblocks_out, const int* flag, cudaStream_t st);
 int tiled_edge_outputs(const mde_edges* e, const float* X, int m, float* distances, float* distortions,
                        cudaStream_t st);
+
+// pull kernel (mde_pull.cu)
+int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_fn_t* fn, int embedding_dim,
+               cudaStream_t st);
+void pull_free(mde_edges* e);
+int pull_launch(int mode, const mde_edges* e, const float* X, int m, float* grad, const float* gext,
+                int* nblocks_out, const int* flag, cudaStream_t st);
+int pull_edge_outputs(const mde_edges* e, const float* X, int m, float* distances, float* distortions,
+                      cudaStream_t st);
 
 }  // namespace mde

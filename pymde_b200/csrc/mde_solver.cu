@@ -44,9 +44,9 @@ namespace {
 
 constexpr int kVecThreads = 256;
 constexpr int kVecBlocks = kNumSMs * 2;
-constexpr int kPairsPerSlice = 8;
-constexpr int kDotsPerSlice = 4 + 5 * kPairsPerSlice;  // 44
-constexpr int kMaxSlices = kMaxMemory / kPairsPerSlice;  // 4
+constexpr int kPairsPerSlice = 10;  // the default history (memory_size = 10, optim.py:110) fits ONE slice: one wave
+constexpr int kDotsPerSlice = 4 + 5 * kPairsPerSlice;  // 54
+constexpr int kMaxSlices = (kMaxMemory + kPairsPerSlice - 1) / kPairsPerSlice;  // 4
 constexpr int kStatusInts = 12;
 enum { PH_DIR = 0, PH_TRIAL = 1, PH_FRESH = 2, PH_MAT = 3 };  // mode 2: phase of a step
 
@@ -179,14 +179,18 @@ constexpr int kScalarSmemBytes = (int)(sizeof(double) * (kMaxSlices * kDotsPerSl
 // ---------------------------------------------------------------------------------------
 // P1: candidate pair + all dot products of the history against (y_c, s_c, g)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kVecThreads)
+__global__ void __launch_bounds__(kVecThreads, 2)
 lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, const float* __restrict__ gprev,
                   const float* __restrict__ d, float* __restrict__ Sb, float* __restrict__ Yb,
                   int64_t npad, double* __restrict__ part, Tail tl, const int* __restrict__ gate) {
   if (off(&S->active)) return;
   if (gate != nullptr && off(gate)) return;
-  __shared__ __align__(16) unsigned char raw[sizeof(float) * kDotsPerSlice * kVecThreads];
+  // reduction tile: 27 rows x 256 threads of fp32 partials (used twice: 54 sums), later the scalar epilogue's scratch
+  constexpr int kHalf = kDotsPerSlice / 2;
+  __shared__ __align__(16) unsigned char raw[sizeof(float) * kHalf * kVecThreads];
   static_assert(sizeof(raw) >= kScalarSmemBytes, "scalar epilogue must fit in the reduction tile");
+  __shared__ const float* sp[kPairsPerSlice];
+  __shared__ const float* yp[kPairsPerSlice];
   const int slice = blockIdx.y;
   const int count = S->lb.count;
   const bool skip = (S->lb.n_iter == 0) || (slice > 0 && slice * kPairsPerSlice >= count);
@@ -194,33 +198,29 @@ lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, cons
   const float t = (float)S->t_last;
   float* sc = Sb + (int64_t)S->lb.cand * npad;
   float* yc = Yb + (int64_t)S->lb.cand * npad;
-  const float* sj[kPairsPerSlice];
-  const float* yj[kPairsPerSlice];
-  bool val[kPairsPerSlice];
-#pragma unroll
-  for (int j = 0; j < kPairsPerSlice; ++j) {
-    int lj = slice * kPairsPerSlice + j;
-    val[j] = lj < count;
-    int q = val[j] ? S->lb.order[lj] : 0;
-    sj[j] = Sb + (int64_t)q * npad;
-    yj[j] = Yb + (int64_t)q * npad;
+  if (threadIdx.x < kPairsPerSlice) {
+    const int lj = slice * kPairsPerSlice + threadIdx.x;
+    const int q = (lj < count) ? S->lb.order[lj] : 0;
+    sp[threadIdx.x] = Sb + (int64_t)q * npad;
+    yp[threadIdx.x] = Yb + (int64_t)q * npad;
   }
+  __syncthreads();
+  int nval = count - slice * kPairsPerSlice;  // pairs of this slice (block-uniform)
+  if (nval > kPairsPerSlice) nval = kPairsPerSlice;
+  // fp32 per-thread partial sums (at the bench size a thread owns ONE float4; at 1e7 rows ~130): the block and
+  // grid stages below run in fp64.  The reference accumulates the same dot products in fp32 end to end.
   float acc[kDotsPerSlice];
 #pragma unroll
   for (int k = 0; k < kDotsPerSlice; ++k) acc[k] = 0.0f;
-  double dacc[kDotsPerSlice];
-#pragma unroll
-  for (int k = 0; k < kDotsPerSlice; ++k) dacc[k] = 0.0;
   const int64_t n4 = npad >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int cnt = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 G = reinterpret_cast<const float4*>(g)[i];
-    float4 P = reinterpret_cast<const float4*>(gprev)[i];
-    float4 D = reinterpret_cast<const float4*>(d)[i];
-    float gv[4] = {G.x, G.y, G.z, G.w};
-    float yv[4] = {G.x - P.x, G.y - P.y, G.z - P.z, G.w - P.w};
-    float sv[4] = {D.x * t, D.y * t, D.z * t, D.w * t};
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    const float4 P = reinterpret_cast<const float4*>(gprev)[i];
+    const float4 D = reinterpret_cast<const float4*>(d)[i];
+    const float gv[4] = {G.x, G.y, G.z, G.w};
+    const float yv[4] = {G.x - P.x, G.y - P.y, G.z - P.z, G.w - P.w};
+    const float sv[4] = {D.x * t, D.y * t, D.z * t, D.w * t};
     if (slice == 0) {
       reinterpret_cast<float4*>(yc)[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
       reinterpret_cast<float4*>(sc)[i] = make_float4(sv[0], sv[1], sv[2], sv[3]);
@@ -232,11 +232,11 @@ lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, cons
     }
 #pragma unroll
     for (int j = 0; j < kPairsPerSlice; ++j) {
-      if (val[j]) {
-        float4 A = reinterpret_cast<const float4*>(sj[j])[i];
-        float4 B = reinterpret_cast<const float4*>(yj[j])[i];
-        float av[4] = {A.x, A.y, A.z, A.w};
-        float bv[4] = {B.x, B.y, B.z, B.w};
+      if (j < nval) {
+        const float4 A = reinterpret_cast<const float4*>(sp[j])[i];
+        const float4 B = reinterpret_cast<const float4*>(yp[j])[i];
+        const float av[4] = {A.x, A.y, A.z, A.w};
+        const float bv[4] = {B.x, B.y, B.z, B.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           acc[4 + 5 * j + 0] += av[q] * yv[q];
@@ -247,30 +247,24 @@ lbfgs_dots_kernel(SolverState* __restrict__ S, const float* __restrict__ g, cons
         }
       }
     }
-    if (++cnt == 16) {
-#pragma unroll
-      for (int k = 0; k < kDotsPerSlice; ++k) { dacc[k] += (double)acc[k]; acc[k] = 0.0f; }
-      cnt = 0;
-    }
   }
-#pragma unroll
-  for (int k = 0; k < kDotsPerSlice; ++k) dacc[k] += (double)acc[k];
-  // block reduction through a transposed shared-memory tile: 44 x 256 fp32 partials, then each
-  // warp sums whole rows in fp64 (8 conflict-free loads per lane + one shuffle tree per row).
-  // ~10x fewer instructions than 44 independent shuffle trees per thread.
+  // block reduction through a transposed shared-memory tile, two halves of 27 sums: each warp sums whole rows in
+  // fp64 (8 conflict-free loads per lane + one shuffle tree per row)
   float (*tile)[kVecThreads] = reinterpret_cast<float (*)[kVecThreads]>(raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* o = part + ((int64_t)slice * gridDim.x + blockIdx.x) * kDotsPerSlice;
 #pragma unroll
-  for (int k = 0; k < kDotsPerSlice; ++k) tile[k][threadIdx.x] = (float)dacc[k];
-  __syncthreads();
-  {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double* o = part + ((int64_t)slice * gridDim.x + blockIdx.x) * kDotsPerSlice;
-    for (int k = w; k < kDotsPerSlice; k += kVecThreads / 32) {
+  for (int h = 0; h < 2; ++h) {
+    if (h) __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kHalf; ++k) tile[k][threadIdx.x] = acc[h * kHalf + k];
+    __syncthreads();
+    for (int k = w; k < kHalf; k += kVecThreads / 32) {
       double sum = 0.0;
 #pragma unroll
       for (int q = 0; q < kVecThreads / 32; ++q) sum += (double)tile[k][lane + 32 * q];
       sum = warp_sum(sum);
-      if (lane == 0) o[k] = sum;
+      if (lane == 0) o[h * kHalf + k] = sum;
     }
   }
   }  // !skip

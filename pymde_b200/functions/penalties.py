@@ -189,6 +189,17 @@ class PushAndPull(Function):
         t.push_pull = 1
         return t, self.weights, None
 
+    def forward(self, distances):
+        # kernel path when both sub-penalties are table functions; otherwise the reference's masked evaluation
+        # (pymde/functions/penalties.py:394-400): any callable class is a legal attractive / repulsive penalty
+        if self._supported():
+            return super(PushAndPull, self).forward(distances)
+        out = torch.zeros_like(distances)
+        pos = self.pos_idx
+        out[pos] = self.attractive_penalty(distances[pos])
+        out[~pos] = self.repulsive_penalty(distances[~pos])
+        return out
+
     def _supported(self):
         a, r = self.attractive_penalty, self.repulsive_penalty
         return (isinstance(a, Function) and isinstance(r, Function) and a._fn_id is not None

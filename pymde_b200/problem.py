@@ -248,12 +248,45 @@ class MDE(torch.nn.Module):
         p.text(self.__str__())
 
     # ---- CUDA path plumbing ------------------------------------------------------------------
+    def __setattr__(self, name, value):
+        # the layout snapshots the distortion function's parameters, the device solver the constraint's:
+        # replacing either must not leave stale device copies behind (the reference re-reads them every evaluation)
+        if name in ("distortion_function", "constraint") and "_edge_layout" in self.__dict__:
+            self._invalidate(layout=(name == "distortion_function"))
+        super(MDE, self).__setattr__(name, value)
+
+    def _invalidate(self, layout=True):
+        cur = self.__dict__.get("_device_solver")
+        if cur is not None:
+            cur[1].close()
+            self.__dict__["_device_solver"] = None
+        if layout:
+            lay = self.__dict__.get("_edge_layout")
+            if lay is not None:
+                lay.close()
+                self.__dict__["_edge_layout"] = None
+
+    @staticmethod
+    def _tensor_stamp(*tensors):
+        """(data_ptr, in-place version, shape) of every tensor: changes when a parameter is mutated or replaced."""
+        return tuple((int(t.data_ptr()), int(t._version), tuple(t.shape)) for t in tensors if isinstance(t, torch.Tensor))
+
+    def _function_stamp(self):
+        if not self._is_table_function():
+            return ("external", id(self.distortion_function))
+        table, par0, par1 = self.distortion_function._table()
+        scal = (table.fn_att, table.fn_rep, tuple(table.att), tuple(table.rep), table.push_pull)
+        return (scal,) + self._tensor_stamp(par0, par1)
+
     def _is_table_function(self):
         f = self.distortion_function
         return isinstance(f, Function) and f._supported()
 
     def _layout(self):
         lay = self.__dict__["_edge_layout"]
+        if lay is not None and lay.stamp != self._function_stamp():
+            self._invalidate(layout=True)  # weights / deviations / scalars were mutated since the layout was built
+            lay = None
         if lay is None:
             if self._is_table_function():
                 table, par0, par1 = self.distortion_function._table()
@@ -265,6 +298,7 @@ class MDE(torch.nn.Module):
             lay = EdgeLayout(self.edges, int(self.n_items), table, par0, par1, self.device, p_total=p_total,
                              embedding_dim=int(self.embedding_dim))
             lay.dist = self.__dict__["_dist"]
+            lay.stamp = self._function_stamp()
             self.__dict__["_edge_layout"] = lay
         return lay
 
@@ -284,20 +318,24 @@ class MDE(torch.nn.Module):
     def _solver(self, constraint, memory_size, max_iter):
         """Device solver for this problem, cached across embed() calls.  `max_iter` only sizes the statistics
         buffers, so a cached solver with enough capacity is reused (its CUDA graphs are built once)."""
-        key = (id(constraint), int(memory_size), optim.DEFAULT_MODE)
+        layout = self._layout()  # (re)built first: a rebuilt layout invalidates the solver that referenced the old one
+        stamp = ()
+        if isinstance(constraint, constraints.Anchored):  # anchor indices / values are copied at solver creation
+            stamp = self._tensor_stamp(constraint.anchors, constraint.values)
+        key = (int(memory_size), optim.DEFAULT_MODE, stamp)
         cur = self.__dict__["_device_solver"]
-        if cur is None or cur[0] != key or cur[1].max_iter < int(max_iter):
+        if cur is None or cur[2] is not constraint or cur[0] != key or cur[1].max_iter < int(max_iter):
             if cur is not None:
                 cur[1].close()
             dist = self.__dict__["_dist"]
             capacity = max(int(max_iter), 1024)
-            solver = optim.DeviceSolver(self._layout(), int(self.n_items), int(self.embedding_dim), constraint,
+            solver = optim.DeviceSolver(layout, int(self.n_items), int(self.embedding_dim), constraint,
                                         memory_size, capacity,
                                         world_size=1 if dist is None else dist["world_size"],
                                         allreduce=None if dist is None else dist.get("allreduce"),
                                         exchange=None if dist is None else dist.get("exchange"),
                                         rank=0 if dist is None else dist["rank"])
-            cur = (key, solver)
+            cur = (key, solver, constraint)  # holds the constraint: a recycled id() can never alias it
             self.__dict__["_device_solver"] = cur
         return cur[1]
 

@@ -246,8 +246,149 @@ def gen_trajectories():
     print("trajectories.npz", len(out))
 
 
+def gen_anchored():
+    """Anchored constraint (pymde/constraints.py:114-164), the 'embedding new points' workflow: 12 anchors keep their
+    values, the other rows are optimised.  (a) Quadratic penalties: converges (convex in the free rows);
+    (b) PushAndPull(Log1p, Log): 40 iterations.  fp32 and fp64 runs of the unmodified reference."""
+    out = {}
+    pen = pymde.penalties
+    rng = np.random.default_rng(21)
+    n, m = 150, 2
+    att = knn_like_graph(n, 4, rng)
+    rep = random_graph(n, len(att), np.random.default_rng(22))
+    anchors = np.sort(rng.choice(n, 12, replace=False)).astype(np.int64)
+    values = rng.standard_normal((12, m)).astype(np.float32) * 2.0
+    out["anchors"], out["values"] = anchors, values
+    cases = {
+        "quad": (att, np.ones(len(att), np.float32) * rng.uniform(0.5, 2.0, len(att)).astype(np.float32),
+                 lambda w: pen.Quadratic(w), 200),
+        "pp": (np.concatenate([att, rep]),
+               np.concatenate([np.ones(len(att)), -np.ones(len(rep))]).astype(np.float32),
+               lambda w: pen.PushAndPull(w, pen.Log1p, pen.Log), 40),
+    }
+    for key, (edges, w, mk, iters) in cases.items():
+        out[key + "/edges"], out[key + "/par0"], out[key + "/max_iter"] = edges, w, np.array(iters)
+        for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            cons = pymde.Anchored(torch.tensor(anchors), torch.tensor(values, dtype=dtype))
+            if tag == "f32":
+                torch.manual_seed(0)
+                X0 = cons.initialization(n, m)
+                out[key + "/X0"] = X0.numpy().copy()
+            else:
+                X0 = torch.tensor(out[key + "/X0"], dtype=dtype)
+            mde = pymde.MDE(n, m, torch.tensor(edges), mk(torch.tensor(w, dtype=dtype)), cons)
+            X = mde.embed(X=X0, max_iter=iters, eps=1e-6)
+            st = mde.solve_stats
+            out["%s/%s/X" % (key, tag)] = X.detach().numpy()
+            out["%s/%s/average_distortions" % (key, tag)] = np.array(st.average_distortions)
+            out["%s/%s/residual_norms" % (key, tag)] = np.array(st.residual_norms)
+            out["%s/%s/final_value" % (key, tag)] = mde.average_distortion(X.detach()).numpy()
+            print("anchored", key, tag, "iters", st.iterations, "final", float(out["%s/%s/final_value" % (key, tag)]))
+    np.savez_compressed(os.path.join(HERE, "anchored.npz"), **out)
+    print("anchored.npz", len(out))
+
+
+def gen_nearzero():
+    """Repulsive and attractive edges at tiny distances: the fast-math kernels switch to a
+    series for 1 - exp(-d) below d = 0.0625 and mask d = 0; the reference (fp32 and fp64) is the arbiter.
+    Points come in clusters of near-duplicates, so edge lengths span 1e-6 .. 1e-1 plus exact zeros."""
+    out = {}
+    pen = pymde.penalties
+    for m in (2, 3):
+        rng = np.random.default_rng(100 + m)
+        n, p = 240, 640
+        centers = rng.standard_normal((n // 8, m)).astype(np.float32)
+        scale = 10.0 ** rng.uniform(-6, -1, n).astype(np.float32)
+        X = (centers[np.arange(n) // 8] + scale[:, None] * rng.standard_normal((n, m)).astype(np.float32)).astype(np.float32)
+        X[1] = X[0]            # exact duplicates: d = 0 on an attractive and on a repulsive edge
+        X[9] = X[8]
+        pairs = set()
+        while len(pairs) < p - 2:
+            c = int(rng.integers(0, n // 8))
+            i, j = rng.integers(0, 8, 2) + 8 * c   # inside a cluster: tiny distance
+            if rng.random() < 0.2:
+                j = int(rng.integers(0, n))        # some ordinary lengths too
+            if i != j and (min(i, j), max(i, j)) not in ((0, 1), (8, 9)):
+                pairs.add((min(i, j), max(i, j)))
+        edges = np.array(sorted(pairs) + [(0, 1), (8, 9)], dtype=np.int64)
+        w = rng.choice([1.0, 2.0, -1.0], len(edges)).astype(np.float32)
+        w[-2], w[-1] = 1.0, -1.0
+        key = "m%d" % m
+        out[key + "/edges"], out[key + "/X"], out[key + "/par0"] = edges, X, w
+        for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            f = pen.PushAndPull(torch.tensor(w, dtype=dtype), pen.Log1p, pen.Log)
+            mde = pymde.MDE(n, m, torch.tensor(edges), f, pymde.Centered())
+            Xt = torch.tensor(X, dtype=dtype, requires_grad=True)
+            d = mde.distances(Xt.detach())
+            keep = d > 0   # the reference's VALUE is -inf on a zero-length repulsive edge; its gradient is defined
+            v = mde.average_distortion(Xt)
+            v.backward()
+            out["%s/%s/grad" % (key, tag)] = Xt.grad.numpy()
+            out["%s/%s/distances" % (key, tag)] = d.numpy()
+            fk = f(d)
+            out["%s/%s/value_nonzero_edges" % (key, tag)] = (fk[keep].sum() / len(edges)).numpy()
+        print("nearzero", key, "min positive d", float(out[key + "/f64/distances"][out[key + "/f64/distances"] > 0].min()))
+    np.savez_compressed(os.path.join(HERE, "nearzero.npz"), **out)
+    print("nearzero.npz", len(out))
+
+
+def gen_c2slice():
+    """C2-scale slice: the bench generator at n = 20 000 (444 024 edges, PushAndPull(Log1p, Log)).
+    (i) Standardized, run by the reference to convergence (eps = 1e-5) with 1, 4 and 8 torch threads: the objective is
+    non-convex and the fp32 scatter order depends on the thread count, so the reference itself converges to different
+    stationary points -- the spread of its final values is part of the fixture; (ii) Centered, 300 iterations (not
+    converged), 1 and 8 threads.  Edges are regenerated by bench.c2_edges (sha1 stored), only X0 / final X travel."""
+    import hashlib
+    import bench
+    out = {}
+    n, m = 20000, 2
+    edges, w = bench.c2_edges(0, n=n, k=15)
+    X0 = bench.initial_iterate(0, n=n)
+    out["edges_sha1"] = np.frombuffer(hashlib.sha1(edges.tobytes() + w.tobytes()).digest(), dtype=np.uint8)
+    out["n_edges"] = np.array(len(edges))
+    pen = pymde.penalties
+    cons = pymde.Standardized()
+    Xs = cons.project_onto_constraint(torch.tensor(X0).clone())
+    out["std/X0"] = Xs.numpy().copy()
+    for th in (8, 4, 1):
+        torch.set_num_threads(th)
+        mde = pymde.MDE(n, m, torch.tensor(edges), pen.PushAndPull(torch.tensor(w), pen.Log1p, pen.Log), cons)
+        X = mde.embed(X=Xs.clone(), max_iter=1500, eps=1e-5)
+        st = mde.solve_stats
+        out["std/t%d/average_distortions" % th] = np.array(st.average_distortions)
+        out["std/t%d/residual_norms" % th] = np.array(st.residual_norms)
+        out["std/t%d/final_value" % th] = mde.average_distortion(X.detach()).numpy()
+        if th == 8:
+            out["std/t8/X"] = X.detach().numpy().copy()
+        print("c2slice std threads", th, "iters", st.iterations, "final", float(out["std/t%d/final_value" % th]))
+    out["cen/X0"] = X0
+    for th in (8, 1):
+        torch.set_num_threads(th)
+        mde = pymde.MDE(n, m, torch.tensor(edges), pen.PushAndPull(torch.tensor(w), pen.Log1p, pen.Log), pymde.Centered())
+        mde.embed(X=torch.tensor(X0), max_iter=300, eps=1e-5)
+        st = mde.solve_stats
+        out["cen/t%d/average_distortions" % th] = np.array(st.average_distortions)
+        out["cen/t%d/residual_norms" % th] = np.array(st.residual_norms)
+        print("c2slice cen threads", th, "iters", st.iterations, "last", st.average_distortions[-1])
+    torch.set_num_threads(1)
+    np.savez_compressed(os.path.join(HERE, "c2slice.npz"), **out)
+    print("c2slice.npz", len(out))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "c2slice":
+        gen_c2slice()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "anchored":
+        gen_anchored()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "nearzero":
+        gen_nearzero()
+        sys.exit(0)
     gen_functions()
     gen_evals()
     gen_projections()
     gen_trajectories()
+    gen_anchored()
+    gen_nearzero()
+    gen_c2slice()

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Worker of tests/test_gpu_multi.py (run under torch.distributed.run, one rank per GPU).
+
+Every rank builds its shard of the SAME problem (pymde_b200.dist.shard_mde) and checks
+  (i)   the sharded evaluation (value AND gradient through autograd) against the C oracle on the whole edge list,
+  (ii)  the sharded solve, peer-memory all-reduce (graph-captured) AND the NCCL host hook: iteration-0 loss and
+        gradient norm against the oracle, first iterations against the single-GPU solve, bit-identical X on all ranks,
+  (iii) a converged problem (quadratic penalties, Standardized): final average distortion within 1e-5 of the
+        single-GPU solve.
+Prints one JSON line `MGPU_RESULT {...}` on rank 0."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as td
+import bench
+import pymde_b200 as pm
+from pymde_b200 import dist as pdist
+from oracle import c_oracle, mde_oracle as O
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
+td.init_process_group("nccl", device_id=dev)
+res = {"world": world}
+n, m = 20000, 2
+edges, w = bench.c2_edges(0, n=n, k=10)
+X0 = bench.initial_iterate(0, n=n, m=m)
+et, wt = torch.tensor(edges), torch.tensor(w)
+mk = lambda lo, hi: pm.penalties.PushAndPull(wt[lo:hi].to(dev), pm.penalties.Log1p, pm.penalties.Log)
+spec = O.FnSpec(O.P_LOG1P, w, (1.5, 0, 0), fn_rep=O.P_LOG, rep=(1.0, 0, 0))
+v_ref, g_ref = c_oracle.average_distortion(X0, edges, spec, True)
+r_ref = float(np.sqrt((g_ref ** 2).sum()))
+
+
+def digests_equal(X):
+    import hashlib
+    d = hashlib.sha1(X.detach().cpu().numpy().tobytes()).hexdigest()
+    out = [None] * world
+    td.all_gather_object(out, d)
+    return len(set(out)) == 1
+
+
+# (i) evaluation outside the solver
+mde = pdist.shard_mde(pm.MDE, n, m, et, mk, pm.Centered(), dev, transport="peer")
+Xg = torch.tensor(X0, device=dev, requires_grad=True)
+v = mde.average_distortion(Xg)
+v.backward()
+res["eval_value_rel"] = abs(v.item() - v_ref) / abs(v_ref)
+res["eval_grad_err"] = float(np.abs(Xg.grad.cpu().numpy() - g_ref).max() / np.abs(g_ref).max())
+
+# (ii) solves
+K = 25
+full_stats = None
+if rank == 0:
+    full = pm.MDE(n, m, et.to(dev), mk(0, len(edges)), pm.Centered(), device=dev)
+    full.embed(X=torch.tensor(X0, device=dev), max_iter=K, eps=0.0)
+    full_stats = np.array(full.solve_stats.average_distortions)
+for transport in ("peer", "nccl"):
+    md = pdist.shard_mde(pm.MDE, n, m, et, mk, pm.Centered(), dev, transport=transport)
+    X = md.embed(X=torch.tensor(X0, device=dev), max_iter=K, eps=0.0)
+    st = md.solve_stats
+    a = np.array(st.average_distortions)
+    r = {"iterations": st.iterations, "x_identical": digests_equal(X),
+         "loss0_rel": abs(a[0] - v_ref) / abs(v_ref), "resid0_rel": abs(st.residual_norms[0] - r_ref) / r_ref,
+         "decreased": bool(a[-1] < 0.5 * a[0]),
+         "peer_memory": bool(md.__dict__["_device_solver"][1].peer_memory)}
+    if rank == 0:
+        r["first3_rel_vs_single"] = float(np.abs(a[:3] - full_stats[:3]).max() / np.abs(full_stats[:3]).max())
+        r["final_rel_vs_single"] = float(abs(a[-1] - full_stats[-1]) / abs(full_stats[-1]))
+    res[transport] = r
+    del md
+
+# (iii) a problem that converges: final value must agree to 1e-5
+rng = np.random.default_rng(1)
+n2, p2 = 3000, 30000
+e2 = rng.integers(0, n2, (p2 * 2, 2)); e2 = e2[e2[:, 0] != e2[:, 1]][:p2]
+w2 = (rng.random(p2).astype(np.float32) + 0.5)
+e2t, w2t = torch.tensor(e2), torch.tensor(w2)
+mk2 = lambda lo, hi: pm.penalties.Quadratic(w2t[lo:hi].to(dev))
+gen = torch.Generator(); gen.manual_seed(0)
+X2 = pm.Standardized().initialization(n2, 2, dev) if False else None
+Xi = torch.randn(n2, 2, generator=gen).to(dev)
+Xi = pm.Standardized().project_onto_constraint(Xi, inplace=True)
+ms = pdist.shard_mde(pm.MDE, n2, 2, e2t, mk2, pm.Standardized(), dev, transport="peer")
+ms.embed(X=Xi, max_iter=400, eps=1e-6)
+conv = {"iterations": ms.solve_stats.iterations, "value": float(ms.solve_stats.average_distortions[-1]),
+        "residual": float(ms.solve_stats.residual_norms[-1]), "x_identical": digests_equal(ms.X)}
+if rank == 0:
+    one = pm.MDE(n2, 2, e2t.to(dev), mk2(0, p2), pm.Standardized(), device=dev)
+    one.embed(X=Xi, max_iter=400, eps=1e-6)
+    conv["single_value"] = float(one.solve_stats.average_distortions[-1])
+    conv["single_iterations"] = one.solve_stats.iterations
+    conv["rel"] = abs(conv["value"] - conv["single_value"]) / abs(conv["single_value"])
+res["converged"] = conv
+if rank == 0:
+    print("MGPU_RESULT " + json.dumps(res), flush=True)
+td.barrier()
+td.destroy_process_group()

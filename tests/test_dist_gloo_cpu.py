@@ -57,3 +57,39 @@ def test_sharded_evaluation_world2():
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert all(ret.get(r, False) for r in range(world)), dict(ret)
+
+
+def _exchange_worker(rank, world, port, ret):
+    sys.path.insert(0, REPO)
+    from pymde_b200 import dist as pdist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = bytes([(rank * 37 + k) % 256 for k in range(64)])
+    got = pdist.make_exchange()(mine)  # what DeviceSolver hands to mde_solver_comm_connect
+    want = b"".join(bytes([(r * 37 + k) % 256 for k in range(64)]) for r in range(world))
+    ret[rank] = (got == want)
+    dist.destroy_process_group()
+
+
+def test_ipc_handle_exchange_world2():
+    """The 64-byte cudaIpc handles reach every rank in rank order (host side of the peer-memory all-reduce)."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_exchange_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert all(ret.get(r, False) for r in range(world)), dict(ret)
+
+
+def test_shard_ranges_cover_and_balance():
+    sys.path.insert(0, REPO)
+    from pymde_b200.dist import shard_range, pack_handles
+    for p in (1, 7, 1000, 1554550):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(p, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == p
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        pack_handles([b"short"])

@@ -304,3 +304,38 @@ def test_full_size_c2_against_c_oracle():
     d = mde.distances(X.detach()).cpu().numpy()
     d_ref = np.linalg.norm(X0[edges[:, 0]].astype(np.float64) - X0[edges[:, 1]].astype(np.float64), axis=1)
     np.testing.assert_allclose(d, d_ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kernel", ["fast", "precise"])
+@pytest.mark.parametrize("layout", [None, "soa", "tiles"])
+@pytest.mark.parametrize("m", [2, 3])
+def test_near_zero_distances_match_reference(golden, m, layout, kernel, monkeypatch):
+    """Edges between near-duplicate points (1e-6 <= d <= 1e-1) and exact duplicates (d = 0), attractive and
+    repulsive: the MUFU kernels' small-d series for 1 - exp(-d) and the d = 0 mask against the reference's fp64
+    run.  The reference's VALUE is -inf when a repulsive edge has d = 0 (log(0)); its gradient is still defined
+    (non-finite coefficient -> 1, zero difference vector), so the value is compared on the edges with d > 0."""
+    pm = _pm()
+    if layout:
+        monkeypatch.setenv("MDE_B200_LAYOUT", layout)
+    if kernel == "precise":
+        monkeypatch.setenv("MDE_B200_KERNEL", "precise")
+    g = golden["nearzero"]
+    key = "m%d" % m
+    edges, X, w = g[key + "/edges"], g[key + "/X"], g[key + "/par0"]
+    f = pm.penalties.PushAndPull(torch.tensor(w, device="cuda"), pm.penalties.Log1p, pm.penalties.Log)
+    mde = pm.MDE(X.shape[0], m, torch.tensor(edges, device="cuda"), f, pm.Centered())
+    Xt = torch.tensor(X, device="cuda", requires_grad=True)
+    d = mde.distances(Xt.detach()).cpu().numpy()
+    np.testing.assert_allclose(d, g[key + "/f32/distances"], rtol=2e-6, atol=1e-9)
+    assert (d == 0).sum() == 2
+    # gradient: defined everywhere
+    keep = torch.tensor(d > 0, device="cuda")
+    sub = pm.MDE(X.shape[0], m, torch.tensor(edges, device="cuda")[keep],
+                 pm.penalties.PushAndPull(torch.tensor(w, device="cuda")[keep], pm.penalties.Log1p, pm.penalties.Log),
+                 pm.Centered())
+    v = sub.average_distortion(Xt) * (int(keep.sum()) / len(edges))  # same divisor as the fixture
+    np.testing.assert_allclose(v.item(), float(g[key + "/f64/value_nonzero_edges"]), rtol=1e-5)
+    mde.average_distortion(Xt).backward()
+    gr = g[key + "/f64/grad"]
+    err = np.abs(Xt.grad.cpu().numpy() - gr).max()
+    assert err <= 3e-5 * np.abs(gr).max(), (err, np.abs(gr).max())

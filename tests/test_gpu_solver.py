@@ -170,6 +170,33 @@ def test_anchored_constraint_keeps_anchors():
     assert mde.solve_stats.average_distortions[-1] < mde.solve_stats.average_distortions[0]
 
 
+@pytest.mark.parametrize("key", ["quad", "pp"])
+def test_anchored_follows_reference_trajectory(golden, key, solver_mode):
+    """Anchored against fixtures generated by the unmodified reference (tests/golden/anchored.npz)."""
+    import pymde_b200 as pm
+    g = golden["anchored"]
+    dev = "cuda"
+    w = torch.tensor(g[key + "/par0"], device=dev)
+    f = pm.penalties.Quadratic(w) if key == "quad" else pm.penalties.PushAndPull(w, pm.penalties.Log1p, pm.penalties.Log)
+    anchors = torch.tensor(g["anchors"], device=dev)
+    values = torch.tensor(g["values"], device=dev)
+    n, m = g[key + "/X0"].shape
+    mde = pm.MDE(n, m, torch.tensor(g[key + "/edges"], device=dev), f, pm.Anchored(anchors, values))
+    X = mde.embed(X=torch.tensor(g[key + "/X0"], device=dev), max_iter=int(g[key + "/max_iter"]), eps=1e-6)
+    st = mde.solve_stats
+    ref = g[key + "/f32/average_distortions"]
+    np.testing.assert_allclose(st.average_distortions[0], ref[0], rtol=1e-5)
+    np.testing.assert_allclose(st.residual_norms[0], g[key + "/f32/residual_norms"][0], rtol=1e-4)
+    k = min(5, len(ref), st.iterations)
+    np.testing.assert_allclose(st.average_distortions[:k], ref[:k], rtol=1e-3)
+    assert torch.equal(X[anchors], values)
+    final = mde.average_distortion(X).item()
+    if key == "quad":  # convex in the free rows: the reference (fp32 and fp64) and this solver meet at the optimum
+        np.testing.assert_allclose(final, float(g["quad/f64/final_value"]), rtol=1e-5)
+    else:
+        np.testing.assert_allclose(final, float(g["pp/f32/final_value"]), rtol=1e-2)
+
+
 def test_custom_constraint_and_callable_use_generic_solver():
     import pymde_b200 as pm
 

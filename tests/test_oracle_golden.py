@@ -201,3 +201,24 @@ def test_gradient_of_average_distortion_matches_central_differences(name, m):
             num[i, c] = (O.average_distortion(Xp, e, spec, False)[0] - O.average_distortion(Xm, e, spec, False)[0]) / (2 * h)
     np.testing.assert_allclose(g, num, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(g.sum(0), 0.0, atol=1e-12)  # translation invariance
+
+
+@pytest.mark.parametrize("key", ["quad", "pp"])
+def test_anchored_trajectory_f64_matches_reference_f64(golden, key):
+    """Anchored constraint (pymde/constraints.py:114-164): tangent projection zeroes the anchor rows, the retraction
+    re-writes them; the float64 restatement follows the reference's float64 embed() iteration for iteration."""
+    g = golden["anchored"]
+    par0 = g[key + "/par0"].astype(np.float64)
+    spec = (O.FnSpec(O.P_QUADRATIC, par0) if key == "quad"
+            else O.FnSpec(O.P_LOG1P, par0, (1.5, 0, 0), fn_rep=O.P_LOG, rep=(1.0, 0, 0)))
+    cons = O.Anchored(g["anchors"], g["values"].astype(np.float64))
+    X, st = O.embed(g[key + "/X0"].astype(np.float64), g[key + "/edges"], spec, cons, eps=1e-6,
+                    max_iter=int(g[key + "/max_iter"]), dtype=np.float64)
+    ref = g[key + "/f64/average_distortions"]
+    assert abs(st.iterations - len(ref)) <= 1
+    k = min(st.iterations, len(ref))
+    np.testing.assert_allclose(st.average_distortions[:k], ref[:k], rtol=1e-6)
+    np.testing.assert_allclose(st.residual_norms[:k], g[key + "/f64/residual_norms"][:k], rtol=1e-4, atol=1e-9)
+    np.testing.assert_array_equal(X[g["anchors"]], g["values"].astype(np.float64))
+    if st.iterations == len(ref):
+        np.testing.assert_allclose(X, g[key + "/f64/X"], atol=1e-4)
