@@ -306,8 +306,8 @@ def kernel_roofline(mde, X0d, m, p_local, n, torch, dev, lib, _lib, cold, profil
     k_ms = float(np.mean(times))
     b_alg = p_local * 12 + 2 * n * m * 4 + 8
     achieved = b_alg / (k_ms * 1e-3) / 1e9
-    prof = load_profile(profile_key)
-    kind = int(lib.mde_edges_kind(lay.handle))
+    kind = int(lib.mde_edges_kind(lay.handle))  # the layout / kernel family the library picked for this workload
+    prof = load_profile("%s:%s" % (profile_key, {0: "soa", 1: "tiles", 2: "pull"}.get(kind, "?")))
     kernel = {0: "distortion_quad_kernel<m=2, fused, LOG1P|LOG, fast-math> (sorted-SoA layout)",
               1: "distortion_tile_kernel<m=2, fused, LOG1P|LOG, fast-math> (tile-record layout, push)",
               2: "distortion_pull_kernel<m=2, fused, LOG1P|LOG, fast-math> (pull-record layout)"}.get(kind, "?")
@@ -381,7 +381,6 @@ def ours_single(args, K, W, torch, pm, _lib, lib, dev, barrier):
     launches0 = lib.mde_launch_count()
     windows, done = timed_windows(solver, K, REPEATS, barrier, torch, dev, 1)
     launches = (lib.mde_launch_count() - launches0) / REPEATS
-    clocks = sampler.stop()
     ms = float(np.median(windows))
     avg, res, pct, stp, fe = solver.stats(done)
 
@@ -404,6 +403,7 @@ def ours_single(args, K, W, torch, pm, _lib, lib, dev, barrier):
     d2h = out_h.numel() * 4 + 4 * 8 * e2e_iters + 48 * (e2e_iters // 64 + 2)  # X, statistics, status words
 
     roofline = kernel_roofline(mde, X0d, EMBED_DIM, p, N_ITEMS, torch, dev, lib, _lib, True, "C2")
+    clocks = sampler.stop()  # sampled across all timed regions above (solver windows, e2e calls, kernel timing)
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

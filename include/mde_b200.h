@@ -206,6 +206,22 @@ int mde_solver_set_allreduce(mde_solver_t* s, mde_allreduce_fn fn, void* user);
 int mde_solver_comm_export(mde_solver_t* s, void* handle_out, int64_t handle_bytes);
 int mde_solver_comm_connect(mde_solver_t* s, int rank, const void* handles, int64_t handle_stride, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Problem construction next to the path.
+ * Hop-count shortest paths of an UNWEIGHTED undirected graph given as a symmetric CSR adjacency (device int32
+ * indptr[n+1], indices[nnz]).  Replaces the one-BFS-per-node pool of pymde/preprocess/graph.py:310-474 and
+ * pymde/preprocess/_graph.pyx:10-52: for every source s in [s_begin, s_end) and every node v > s reachable in
+ * <= max_length hops (0 = unlimited), the triple (s, v, hops) is kept with probability `retain` (counter-based
+ * hash of (seed, s, v)) and appended to out_src / out_dst / out_len (capacity `cap`, unsorted).  *count_dev
+ * (device, caller zeroes it) receives the number of triples produced; if it exceeds `cap` the surplus was dropped
+ * and the caller re-runs with larger buffers.  Blocking (one status read per BFS level).
+ * `ws` >= mde_graph_hops_ws_bytes(n) bytes of device scratch. */
+int64_t mde_graph_hops_ws_bytes(int64_t n);
+int mde_graph_hops(const int32_t* indptr, const int32_t* indices, int64_t n, int64_t s_begin, int64_t s_end,
+                   int max_length, double retain, uint64_t seed, int32_t* out_src, int32_t* out_dst,
+                   float* out_len, int64_t cap, unsigned long long* count_dev, void* ws, int64_t ws_bytes,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

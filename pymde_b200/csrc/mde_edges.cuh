@@ -43,11 +43,13 @@ struct mde_edges {
   int nbkt = 0;            // non-empty buckets
   int32_t* bkt_tile = nullptr;  // [nbkt]     dst tile of bucket b
   int32_t* bkt_wt0 = nullptr;   // [nbkt + 1] first warp-tile of bucket b
+  int gred = 0;                 // kind 1: dst contributions as global reds instead of shared-memory CAS
   int ncta = 0;                 // persistent grid of the tile kernel
   int32_t* cta_wt0 = nullptr;   // [ncta + 1] warp-tile range of CTA c
   int32_t* cta_bkt0 = nullptr;  // [ncta]     bucket holding cta_wt0[c]
   // ---- kind 2 (pull records, mde_pull.cu): same bucket / CTA tables, 1040-byte records of DIRECTED entries ----
   int32_t* wt_tile = nullptr;   // [nwt] neighbour tile of every warp-tile (per-edge outputs)
+  int epl = 4;                  // entries per lane per warp-tile (a warp-tile holds 32 * epl entries)
 };
 
 namespace mde {

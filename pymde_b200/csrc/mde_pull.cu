@@ -33,8 +33,9 @@ namespace {
 
 constexpr int kPullWarps = 32;
 constexpr int kPullThreads = kPullWarps * 32;
-constexpr int kRecWords = 260;            // 128 w + 64 (owner u16 x 128) + 64 (nbr u16 x 128) + 4 header
-constexpr int kRecBytes = kRecWords * 4;  // 1040
+// a warp-tile holds NE = 32 * EPL entries (EPL = entries per lane per iteration: 4 or 8); record = 2 NE + 4 words
+__host__ __device__ constexpr int rec_words(int epl) { return 64 * epl + 4; }
+__host__ __device__ constexpr int rec_bytes(int epl) { return rec_words(epl) * 4; }  // 1040 (EPL 4) / 2064 (EPL 8)
 
 template <int M> struct PRow { float v[M]; };
 
@@ -113,14 +114,14 @@ struct PullArgs {
   int x_vec_ok;
 };
 
-// the 4 CONSECUTIVE entries of one lane (slots 4 lane .. 4 lane + 3 of a warp-tile), class known.  Entries are
-// sorted by owner: the lane keeps the sum of a run of equal owners in registers and issues one vector red when the
-// owner changes (and one at the end), so a long run costs one red per lane that holds a piece of it.
+// 4 CONSECUTIVE entries of one lane, class known.  Entries are sorted by owner: the lane keeps the sum of a run of
+// equal owners in registers (`cur`, `acc`, carried across the quads of one warp-tile) and issues one vector red when
+// the owner changes, so a long run costs one red per lane that holds a piece of it.
 template <int M, int MODE, int FA, int FR, bool FAST, int CLS>
-__device__ __forceinline__ void pull_tile_compute(const PullArgs& a, const float* __restrict__ Xt, int ibase, int lane,
-                                                  int own_base, int cnt, const float (&w)[4], const int (&oo)[4],
-                                                  const int (&nl)[4], const float (&gx)[4], float& lsum_f,
-                                                  double& lsum) {
+__device__ __forceinline__ void pull_quad(const PullArgs& a, const float* __restrict__ Xt, int ibase, int first_idx,
+                                          int own_base, int cnt, const float (&w)[4], const int (&oo)[4],
+                                          const int (&nl)[4], const float (&gx)[4], int& cur, float (&acc)[M],
+                                          float& lsum_f, double& lsum) {
   PRow<M> xi[4], xj[4];
   int own[4];
 #pragma unroll
@@ -129,13 +130,9 @@ __device__ __forceinline__ void pull_tile_compute(const PullArgs& a, const float
     xi[e] = p_ldg_row<M>(a.X, own[e]);
     xj[e] = p_lds_row<M>(Xt, nl[e]);
   }
-  float acc[M];
-#pragma unroll
-  for (int c = 0; c < M; ++c) acc[c] = 0.0f;
-  int cur = own[0];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const bool ok = (4 * lane + e) < cnt;
+    const bool ok = (first_idx + e) < cnt;
     float diff[M];
     float d2 = 0.0f;
 #pragma unroll
@@ -169,13 +166,13 @@ __device__ __forceinline__ void pull_tile_compute(const PullArgs& a, const float
       for (int c = 0; c < M; ++c) acc[c] += live ? g * diff[c] : 0.0f;
     }
   }
-  if (MODE != 1 && (4 * lane) < cnt) p_red_row<M>(a.grad, cur, acc);
-  if (FAST) { lsum += (double)lsum_f; lsum_f = 0.0f; }
 }
 
-template <int M, int MODE, int FA, int FR, bool FAST>
+template <int M, int MODE, int FA, int FR, bool FAST, int EPL>
 __global__ void __launch_bounds__(kPullThreads, 1)
 distortion_pull_kernel(const PullArgs a) {
+  constexpr int NE = 32 * EPL;
+  constexpr int kRecWords = rec_words(EPL), kRecBytes = rec_bytes(EPL);
   if (a.flag != nullptr && *a.flag == 0) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int R = 1 << a.rb;
@@ -250,24 +247,35 @@ distortion_pull_kernel(const PullArgs a) {
   for (; t < wt1; t += kPullWarps) {
     mbar_wait(my_bar, ph);
     ph ^= 1;
-    float w[4];
-    int oo[4], nl[4];
+    float w[EPL];
+    uint32_t op[EPL / 2], np_[EPL / 2];  // packed u16 pairs: owner offsets, neighbour rows
     int own_base, cnt, cls;
     {
       const uint32_t q = my_slot;
-      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(own_base) : "r"(q + 1024u));
-      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cnt) : "r"(q + 1028u));
-      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cls) : "r"(q + 1032u));
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(q + 16u * (uint32_t)lane));
-      uint32_t o01, o23, n01, n23;
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o01), "=r"(o23) : "r"(q + 512u + 8u * (uint32_t)lane));
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(n01), "=r"(n23) : "r"(q + 768u + 8u * (uint32_t)lane));
-      oo[0] = (int)(o01 & 0xffffu); oo[1] = (int)(o01 >> 16); oo[2] = (int)(o23 & 0xffffu); oo[3] = (int)(o23 >> 16);
-      nl[0] = (int)(n01 & 0xffffu); nl[1] = (int)(n01 >> 16); nl[2] = (int)(n23 & 0xffffu); nl[3] = (int)(n23 >> 16);
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(own_base) : "r"(q + 8u * NE));
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cnt) : "r"(q + 8u * NE + 4u));
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cls) : "r"(q + 8u * NE + 8u));
+#pragma unroll
+      for (int h = 0; h < EPL / 4; ++h)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[4 * h]), "=f"(w[4 * h + 1]), "=f"(w[4 * h + 2]), "=f"(w[4 * h + 3])
+                     : "r"(q + (uint32_t)(4 * EPL) * (uint32_t)lane + 16u * h));
+      if constexpr (EPL == 4) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(op[0]), "=r"(op[1]) : "r"(q + 4u * NE + 8u * (uint32_t)lane));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(np_[0]), "=r"(np_[1]) : "r"(q + 6u * NE + 8u * (uint32_t)lane));
+      } else {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(op[0]), "=r"(op[1]), "=r"(op[2]), "=r"(op[3]) : "r"(q + 4u * NE + 16u * (uint32_t)lane));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(np_[0]), "=r"(np_[1]), "=r"(np_[2]), "=r"(np_[3]) : "r"(q + 6u * NE + 16u * (uint32_t)lane));
+      }
     }
-    __syncwarp();
+    // WAR on the slot: the next record may only be requested once EVERY lane's loads have returned.  A lane
+    // issues the ballot only after it has consumed one element of each vector load (scoreboard wait), and the ballot
+    // completes only when all lanes have issued it; its result feeds a never-taken branch so it cannot be removed.
+    {
+      unsigned chk = __float_as_uint(w[EPL - 1]) ^ __float_as_uint(w[3]) ^ op[EPL / 2 - 1] ^ np_[EPL / 2 - 1] ^
+                     (unsigned)(own_base ^ cnt ^ cls);
+      if (__ballot_sync(kFull, chk == 0x7fc12345u) == 0x80000001u) lsum += 1e-300;
+    }
     if (lane == 0 && t + kPullWarps < wt1) {  // refill the slot: the record is in registers now
-      fence_proxy_async();
       mbar_expect_tx(my_bar, kRecBytes);
       bulk_g2s_hint(my_slot, a.rec + (int64_t)(t + kPullWarps) * kRecWords, kRecBytes, my_bar, pol);
     }
@@ -276,20 +284,33 @@ distortion_pull_kernel(const PullArgs a) {
       enter_bucket();
       first = false;
     }
-    float gx[4] = {0.f, 0.f, 0.f, 0.f};
-    if (MODE == 2) {
+    float acc[M];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int o = __ldg(a.perm + ((int64_t)t * 128 + 4 * lane + e));
-        gx[e] = __ldg(a.gext + (o > 0 ? (o >> 1) : 0));
+    for (int c = 0; c < M; ++c) acc[c] = 0.0f;
+    int cur = own_base + (int)(op[0] & 0xffffu);
+#pragma unroll
+    for (int h = 0; h < EPL / 4; ++h) {
+      const float wq[4] = {w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]};
+      const int oq[4] = {(int)(op[2 * h] & 0xffffu), (int)(op[2 * h] >> 16), (int)(op[2 * h + 1] & 0xffffu), (int)(op[2 * h + 1] >> 16)};
+      const int nq[4] = {(int)(np_[2 * h] & 0xffffu), (int)(np_[2 * h] >> 16), (int)(np_[2 * h + 1] & 0xffffu), (int)(np_[2 * h + 1] >> 16)};
+      float gx[4] = {0.f, 0.f, 0.f, 0.f};
+      const int first_idx = EPL * lane + 4 * h;
+      if (MODE == 2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int o = __ldg(a.perm + ((int64_t)t * NE + first_idx + e));
+          gx[e] = __ldg(a.gext + (o > 0 ? (o >> 1) : 0));
+        }
+      }
+      if (FAST) {
+        if (cls == 0) pull_quad<M, MODE, FA, FR, FAST, 0>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
+        else pull_quad<M, MODE, FA, FR, FAST, 1>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
+      } else {
+        pull_quad<M, MODE, FA, FR, FAST, 2>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
       }
     }
-    if (FAST) {
-      if (cls == 0) pull_tile_compute<M, MODE, FA, FR, FAST, 0>(a, Xt, (int)base, lane, own_base, cnt, w, oo, nl, gx, lsum_f, lsum);
-      else pull_tile_compute<M, MODE, FA, FR, FAST, 1>(a, Xt, (int)base, lane, own_base, cnt, w, oo, nl, gx, lsum_f, lsum);
-    } else {
-      pull_tile_compute<M, MODE, FA, FR, FAST, 2>(a, Xt, (int)base, lane, own_base, cnt, w, oo, nl, gx, lsum_f, lsum);
-    }
+    if (MODE != 1 && (EPL * lane) < cnt) p_red_row<M>(a.grad, cur, acc);
+    if (FAST) { lsum += (double)lsum_f; lsum_f = 0.0f; }
   }
   if (first && wt0 < wt1) { enter_bucket(); first = false; }
   while (seg_end < wt1) { ++bkt; enter_bucket(); }
@@ -329,17 +350,19 @@ __global__ void pull_starts_kernel(const uint64_t* __restrict__ keys, int64_t p2
   if (k == 0 || (keys[k - 1] >> shift_bkt) != b) start[b] = (int32_t)k;
 }
 
-__global__ void pull_fill_kernel(int32_t* __restrict__ rec, int32_t* __restrict__ perm, int64_t nwt) {
+__global__ void pull_fill_kernel(int32_t* __restrict__ rec, int32_t* __restrict__ perm, int64_t nwt, int epl) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nwt * kRecWords) rec[k] = 0;
-  if (k < nwt * 128) perm[k] = -1;
+  if (k < nwt * rec_words(epl)) rec[k] = 0;
+  if (k < nwt * 32 * epl) perm[k] = -1;
 }
 
 // one thread per sorted entry: write its three fields; the first entry of a warp-tile also writes the header
 __global__ void pull_scatter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                     const float* __restrict__ par0, int64_t p2, PKeyBits kb,
                                     const int32_t* __restrict__ slot_shift, const int32_t* __restrict__ grp_end,
-                                    int32_t* __restrict__ rec, int32_t* __restrict__ perm, int* __restrict__ bad) {
+                                    int32_t* __restrict__ rec, int32_t* __restrict__ perm, int* __restrict__ bad,
+                                    int epl) {
+  const int NE = 32 * epl, kRecWords = rec_words(epl);
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= p2) return;
   const uint64_t key = keys[k];
@@ -349,50 +372,51 @@ __global__ void pull_scatter_kernel(const uint64_t* __restrict__ keys, const uin
   const int32_t nl = (int32_t)(key & ((1ull << kb.rb) - 1ull));
   const uint32_t v = vals[k];
   const int64_t slot = k + (int64_t)slot_shift[b];
-  const int64_t t = slot >> 7;
-  const int j = (int)(slot & 127);
+  const int64_t t = slot / NE;
+  const int j = (int)(slot % NE);
   const int64_t k0 = k - j;  // first entry of this warp-tile (same group: groups start on warp-tile boundaries)
   const int32_t own0 = (int32_t)((keys[k0] >> kb.rb) & own_mask);
   const int32_t off = own - own0;
   if (off < 0 || off > 65535) *bad = 1;
   int32_t* r = rec + t * kRecWords;
   r[j] = __float_as_int(par0[v >> 1]);
-  reinterpret_cast<unsigned short*>(r + 128)[j] = (unsigned short)off;
-  reinterpret_cast<unsigned short*>(r + 192)[j] = (unsigned short)nl;
+  reinterpret_cast<unsigned short*>(r + NE)[j] = (unsigned short)off;
+  reinterpret_cast<unsigned short*>(r + NE + NE / 2)[j] = (unsigned short)nl;
   perm[slot] = (int32_t)v;
   if (j == 0) {
     const int64_t left = (int64_t)grp_end[b] - k0;
-    const int cnt = (int)(left < 128 ? left : 128);
-    r[256] = own0;
-    r[257] = cnt;
-    r[258] = (int32_t)(b & 1ull);
-    r[259] = 0;
+    const int cnt = (int)(left < NE ? left : NE);
+    r[2 * NE] = own0;
+    r[2 * NE + 1] = cnt;
+    r[2 * NE + 2] = (int32_t)(b & 1ull);
+    r[2 * NE + 3] = 0;
     // pads of a partial warp-tile repeat the last valid owner / neighbour so that they extend the last run
-    if (cnt < 128) {
+    if (cnt < NE) {
       const uint64_t kl = keys[k0 + cnt - 1];
       const unsigned short lo = (unsigned short)((int32_t)((kl >> kb.rb) & own_mask) - own0);
       const unsigned short ln = (unsigned short)(kl & ((1ull << kb.rb) - 1ull));
-      for (int q = cnt; q < 128; ++q) {
-        reinterpret_cast<unsigned short*>(r + 128)[q] = lo;
-        reinterpret_cast<unsigned short*>(r + 192)[q] = ln;
+      for (int q = cnt; q < NE; ++q) {
+        reinterpret_cast<unsigned short*>(r + NE)[q] = lo;
+        reinterpret_cast<unsigned short*>(r + NE + NE / 2)[q] = ln;
       }
     }
   }
 }
 
 __global__ void pull_outputs_kernel(const int32_t* __restrict__ rec, const int32_t* __restrict__ perm,
-                                    const int32_t* __restrict__ wt_tile, int rb, int64_t nslots, int m,
+                                    const int32_t* __restrict__ wt_tile, int rb, int epl, int64_t nslots, int m,
                                     const float* __restrict__ X, float* __restrict__ distances,
                                     float* __restrict__ distortions, FnDev fn) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nslots) return;
   const int o = perm[k];
   if (o < 0 || (o & 1)) return;  // pads, and the second direction of every edge
-  const int64_t t = k >> 7;
-  const int j = (int)(k & 127);
-  const int32_t* r = rec + t * kRecWords;
-  const int s = r[256] + (int)reinterpret_cast<const unsigned short*>(r + 128)[j];
-  const int d_ = (wt_tile[t] << rb) + (int)reinterpret_cast<const unsigned short*>(r + 192)[j];
+  const int NE = 32 * epl;
+  const int64_t t = k / NE;
+  const int j = (int)(k % NE);
+  const int32_t* r = rec + t * rec_words(epl);
+  const int s = r[2 * NE] + (int)reinterpret_cast<const unsigned short*>(r + NE)[j];
+  const int d_ = (wt_tile[t] << rb) + (int)reinterpret_cast<const unsigned short*>(r + NE + NE / 2)[j];
   float d2 = 0.0f;
   for (int c = 0; c < m; ++c) {
     const float df = __ldg(X + (int64_t)s * m + c) - __ldg(X + (int64_t)d_ * m + c);
@@ -416,45 +440,48 @@ int penv_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-size_t pull_smem_bytes(int rb, int m) {
-  return (size_t)((size_t)1 << rb) * m * sizeof(float) + (size_t)kPullWarps * kRecBytes +
+size_t pull_smem_bytes(int rb, int m, int epl) {
+  return (size_t)((size_t)1 << rb) * m * sizeof(float) + (size_t)kPullWarps * rec_bytes(epl) +
          (size_t)(kPullWarps + 2) * sizeof(uint64_t) + 32 * sizeof(double);
 }
 
 template <int M, int MODE, int FA, int FR, bool FAST>
-const void* pkptr() { return reinterpret_cast<const void*>(&distortion_pull_kernel<M, MODE, FA, FR, FAST>); }
+const void* pkptr(int epl) {
+  if (epl == 8) return reinterpret_cast<const void*>(&distortion_pull_kernel<M, MODE, FA, FR, FAST, 8>);
+  return reinterpret_cast<const void*>(&distortion_pull_kernel<M, MODE, FA, FR, FAST, 4>);
+}
 
 template <int M, int MODE>
-const void* pselect_m(const FnDev& fn) {
+const void* pselect_m(const FnDev& fn, int epl) {
   const int fa = fn.fn_att, fr = fn.fn_rep, pp = fn.push_pull;
   if constexpr (MODE == 0 && (M == 2 || M == 3)) {
     const char* ev = getenv("MDE_B200_KERNEL");
     const bool precise = ev && !strcmp(ev, "precise");
     const bool hot = pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOG && fn.a0 == 1.5f && fn.r0 == 1.0f && !precise;
-    if (hot) return pkptr<M, MODE, MDE_FN_P_LOG1P, MDE_FN_P_LOG, true>();
-    if (pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOG) return pkptr<M, MODE, MDE_FN_P_LOG1P, MDE_FN_P_LOG, false>();
-    if (pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOGRATIO) return pkptr<M, MODE, MDE_FN_P_LOG1P, MDE_FN_P_LOGRATIO, false>();
-    if (!pp && fa == MDE_FN_P_QUADRATIC) return pkptr<M, MODE, MDE_FN_P_QUADRATIC, MDE_FN_P_QUADRATIC, false>();
-    if (!pp && fa == MDE_FN_L_ABSOLUTE) return pkptr<M, MODE, MDE_FN_L_ABSOLUTE, MDE_FN_L_ABSOLUTE, false>();
-    if (!pp && fa == MDE_FN_L_QUADRATIC) return pkptr<M, MODE, MDE_FN_L_QUADRATIC, MDE_FN_L_QUADRATIC, false>();
-    if (!pp && fa == MDE_FN_L_HUBER) return pkptr<M, MODE, MDE_FN_L_HUBER, MDE_FN_L_HUBER, false>();
+    if (hot) return pkptr<M, MODE, MDE_FN_P_LOG1P, MDE_FN_P_LOG, true>(epl);
+    if (pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOG) return pkptr<M, MODE, MDE_FN_P_LOG1P, MDE_FN_P_LOG, false>(epl);
+    if (pp && fa == MDE_FN_P_LOG1P && fr == MDE_FN_P_LOGRATIO) return pkptr<M, MODE, MDE_FN_P_LOG1P, MDE_FN_P_LOGRATIO, false>(epl);
+    if (!pp && fa == MDE_FN_P_QUADRATIC) return pkptr<M, MODE, MDE_FN_P_QUADRATIC, MDE_FN_P_QUADRATIC, false>(epl);
+    if (!pp && fa == MDE_FN_L_ABSOLUTE) return pkptr<M, MODE, MDE_FN_L_ABSOLUTE, MDE_FN_L_ABSOLUTE, false>(epl);
+    if (!pp && fa == MDE_FN_L_QUADRATIC) return pkptr<M, MODE, MDE_FN_L_QUADRATIC, MDE_FN_L_QUADRATIC, false>(epl);
+    if (!pp && fa == MDE_FN_L_HUBER) return pkptr<M, MODE, MDE_FN_L_HUBER, MDE_FN_L_HUBER, false>(epl);
   }
-  return pkptr<M, MODE, -1, -1, false>();
+  return pkptr<M, MODE, -1, -1, false>(epl);
 }
 template <int MODE>
-const void* pselect_mode(const FnDev& fn, int m) {
+const void* pselect_mode(const FnDev& fn, int m, int epl) {
   switch (m) {
-    case 1: return pselect_m<1, MODE>(fn);
-    case 2: return pselect_m<2, MODE>(fn);
-    case 3: return pselect_m<3, MODE>(fn);
-    case 4: return pselect_m<4, MODE>(fn);
+    case 1: return pselect_m<1, MODE>(fn, epl);
+    case 2: return pselect_m<2, MODE>(fn, epl);
+    case 3: return pselect_m<3, MODE>(fn, epl);
+    case 4: return pselect_m<4, MODE>(fn, epl);
   }
   return nullptr;
 }
-const void* pselect_kernel(const FnDev& fn, int m, int mode) {
-  if (mode == 0) return pselect_mode<0>(fn, m);
-  if (mode == 1) return pselect_mode<1>(fn, m);
-  return pselect_mode<2>(fn, m);
+const void* pselect_kernel(const FnDev& fn, int m, int mode, int epl) {
+  if (mode == 0) return pselect_mode<0>(fn, m, epl);
+  if (mode == 1) return pselect_mode<1>(fn, m, epl);
+  return pselect_mode<2>(fn, m, epl);
 }
 int pconfigure_kernel(const void* k) {
   static std::vector<const void*> done;
@@ -481,7 +508,9 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
   const int64_t p2 = 2 * p;
   int rb = (m <= 2) ? 13 : 12;  // X tile of 64 KB (m = 1: 32 KB)
   { const int r = penv_int("MDE_B200_TILE_RB", 0); if (r >= 8 && r <= 15) rb = r; }
-  if (rb > 16 || pull_smem_bytes(rb, m) > 227u * 1024u) return MDE_E_UNSUPPORTED;
+  const int epl = penv_int("MDE_B200_PULL_EPL", 8) == 4 ? 4 : 8;  // entries per lane per warp-tile
+  const int NE = 32 * epl, kRecWords = rec_words(epl), kRecBytes = rec_bytes(epl);
+  if (rb > 16 || pull_smem_bytes(rb, m, epl) > 227u * 1024u) return MDE_E_UNSUPPORTED;
   int64_t l2_bytes = (int64_t)penv_int("MDE_B200_STILE_MB", 48) << 20;
   int ss = rb;
   while (((int64_t)1 << (ss + 1)) * m * 8 <= l2_bytes && ss < 30) ++ss;
@@ -538,18 +567,18 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
       if (prev_b >= 0) {
         gend[prev_b] = start[b];
         const int64_t cnt = (int64_t)start[b] - (int64_t)start[prev_b];
-        slot += (cnt + 127) / 128 * 128;
+        slot += (cnt + NE - 1) / NE * NE;
       }
       bkt_tile.push_back((int32_t)((b >> 1) % ndt));
-      bkt_wt0.push_back((int32_t)(slot / 128));
+      bkt_wt0.push_back((int32_t)(slot / NE));
       shift[b] = (int32_t)(slot - (int64_t)start[b]);
       prev_b = b;
     }
     if (prev_b < 0) { rc = MDE_E_INVALID; goto done; }
     gend[prev_b] = (int32_t)p2;
-    slot += (p2 - (int64_t)start[prev_b] + 127) / 128 * 128;
+    slot += (p2 - (int64_t)start[prev_b] + NE - 1) / NE * NE;
     if (slot >= (1ll << 31)) { rc = MDE_E_UNSUPPORTED; goto done; }
-    const int64_t nwt = slot / 128;
+    const int64_t nwt = slot / NE;
     bkt_wt0.push_back((int32_t)nwt);
     const int nbkt = (int)bkt_tile.size();
     const int64_t min_per_bucket = penv_int("MDE_B200_TILE_MIN", 2048);
@@ -568,7 +597,7 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
       for (int32_t t = bkt_wt0[b]; t < bkt_wt0[b + 1]; ++t) wt_tile[t] = bkt_tile[b];
 
     TRY(cudaMalloc(&e->rec, sizeof(int32_t) * nwt * kRecWords));
-    TRY(cudaMalloc(&e->perm, sizeof(int32_t) * nwt * 128));
+    TRY(cudaMalloc(&e->perm, sizeof(int32_t) * nwt * NE));
     TRY(cudaMalloc(&e->bkt_tile, sizeof(int32_t) * nbkt));
     TRY(cudaMalloc(&e->bkt_wt0, sizeof(int32_t) * (nbkt + 1)));
     TRY(cudaMalloc(&e->cta_wt0, sizeof(int32_t) * (ncta + 1)));
@@ -581,10 +610,10 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
     TRY(cudaMemcpyAsync(e->cta_wt0, cta_wt0.data(), sizeof(int32_t) * (ncta + 1), cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(e->cta_bkt0, cta_bkt0.data(), sizeof(int32_t) * ncta, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(e->wt_tile, wt_tile.data(), sizeof(int32_t) * nwt, cudaMemcpyHostToDevice, st));
-    pull_fill_kernel<<<ceil_div_i64(nwt * kRecWords, tb), tb, 0, st>>>(e->rec, e->perm, nwt);
+    pull_fill_kernel<<<ceil_div_i64(nwt * kRecWords, tb), tb, 0, st>>>(e->rec, e->perm, nwt, epl);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());
-    pull_scatter_kernel<<<nbk, tb, 0, st>>>(keys_out, vals_out, par0, p2, kb, shift_d, end_d, e->rec, e->perm, bad_d);
+    pull_scatter_kernel<<<nbk, tb, 0, st>>>(keys_out, vals_out, par0, p2, kb, shift_d, end_d, e->rec, e->perm, bad_d, epl);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());
     int bad = 0;
@@ -593,12 +622,13 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
     if (bad) { rc = MDE_E_UNSUPPORTED; goto done; }  // a warp-tile spans more than 65 536 owner rows (very sparse)
     e->fn = to_dev(*fn);
     for (int mode = 0; mode < 3; ++mode) {
-      const void* k = pselect_kernel(e->fn, m, mode);
+      const void* k = pselect_kernel(e->fn, m, mode, epl);
       if (!k) { rc = MDE_E_UNSUPPORTED; goto done; }
       if ((rc = pconfigure_kernel(k))) goto done;
     }
+    e->epl = epl;
     e->kind = 2; e->m_hint = m; e->rb = rb; e->ss = ss; e->nwt = nwt; e->nbkt = nbkt; e->ncta = ncta;
-    e->nbytes = nwt * (kRecBytes + 4 * 128 + 4) + 8 * kMaxLossBlocks + 4ll * (2 * nbkt + 2 * ncta + 2);
+    e->nbytes = nwt * (kRecBytes + 4 * NE + 4) + 8 * kMaxLossBlocks + 4ll * (2 * nbkt + 2 * ncta + 2);
   }
 done:
   cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(vals_out); cudaFree(start_d); cudaFree(shift_d);
@@ -617,14 +647,14 @@ done:
 int pull_launch(int mode, const mde_edges* e, const float* X, int m, float* grad, const float* gext,
                 int* nblocks_out, const int* flag, cudaStream_t st) {
   if (e->kind != 2 || m < 1 || m > 4) return MDE_E_UNSUPPORTED;
-  const size_t smem = pull_smem_bytes(e->rb, m);
+  const size_t smem = pull_smem_bytes(e->rb, m, e->epl);
   if (smem > 227u * 1024u) return MDE_E_UNSUPPORTED;
   PullArgs a;
   a.rec = e->rec; a.perm = e->perm; a.gext = gext; a.bkt_tile = e->bkt_tile; a.bkt_wt0 = e->bkt_wt0;
   a.cta_wt0 = e->cta_wt0; a.cta_bkt0 = e->cta_bkt0; a.X = X; a.grad = grad; a.loss_partials = e->loss_partials;
   a.flag = flag; a.fn = e->fn; a.inv_p = 1.0f / (float)e->p_total; a.n = e->n; a.rb = e->rb;
   a.x_vec_ok = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) ? 1 : 0;
-  const void* k = pselect_kernel(e->fn, m, mode);
+  const void* k = pselect_kernel(e->fn, m, mode, e->epl);
   if (!k) return MDE_E_UNSUPPORTED;
   int rc = pconfigure_kernel(k);
   if (rc) return rc;
@@ -637,9 +667,9 @@ int pull_launch(int mode, const mde_edges* e, const float* X, int m, float* grad
 
 int pull_edge_outputs(const mde_edges* e, const float* X, int m, float* distances, float* distortions,
                       cudaStream_t st) {
-  const int64_t nslots = e->nwt * 128;
+  const int64_t nslots = e->nwt * 32 * e->epl;
   const int tb = 256;
-  pull_outputs_kernel<<<ceil_div_i64(nslots, tb), tb, 0, st>>>(e->rec, e->perm, e->wt_tile, e->rb, nslots, m, X,
+  pull_outputs_kernel<<<ceil_div_i64(nslots, tb), tb, 0, st>>>(e->rec, e->perm, e->wt_tile, e->rb, e->epl, nslots, m, X,
                                                               distances, distortions, e->fn);
   MDE_LAUNCH_CHECK();
   return 0;

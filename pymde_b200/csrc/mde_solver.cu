@@ -692,11 +692,9 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) {  // never served from a stale L1 line
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
+// peer rows are read with ld.global.cg: never served from a (possibly stale) L1 line, and -- unlike a volatile
+// load -- free to be batched, so a thread keeps several NVLink requests in flight
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 // tell every rank "my epoch for this flag kind is `v`" (threads 0..W-1 of one block)
 __device__ __forceinline__ void comm_signal(unsigned* const* flags, const Comm& c, unsigned v) {
@@ -746,34 +744,50 @@ allreduce_kernel(const int* __restrict__ flag, Comm c, float* __restrict__ g, in
   const int64_t n4 = npad >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (PHASE == 0) {
-    for (int64_t i = tid; i < n4; i += stride) {
-      float4 acc = ld_peer_f4(c.buf[0] + 4 * i);
-      for (int q = 1; q < c.world; ++q) {
-        const float4 v = ld_peer_f4(c.buf[q] + 4 * i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  constexpr int U = 4;  // float4 per thread per trip: U * world independent 16-byte loads in flight
+  if (PHASE == 0 || PHASE == 1) {
+    // chunk q = [q * cs, min((q + 1) * cs, n4)) in float4 units; one-shot reduces everything, reduce-scatter its chunk
+    const int64_t cs = (n4 + c.world - 1) / c.world;
+    const int64_t lo = (PHASE == 0) ? 0 : (int64_t)c.rank * cs;
+    const int64_t hi = (PHASE == 0) ? n4 : ((lo + cs < n4) ? lo + cs : n4);
+    float* out = (PHASE == 0) ? g : c.buf[c.rank];
+    for (int64_t i0 = lo + tid; i0 < hi; i0 += U * stride) {
+      float4 acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        acc[u] = (i < hi) ? ld_peer_f4(c.buf[0] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      reinterpret_cast<float4*>(g)[i] = acc;
+      for (int q = 1; q < c.world; ++q) {  // rank order: bit-identical sums on every rank
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = i0 + u * stride;
+          v[u] = (i < hi) ? ld_peer_f4(c.buf[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < hi) reinterpret_cast<float4*>(out)[i] = acc[u];
+      }
     }
     if (tid == 0) comm_reduce_tail(c, npad, g + npad);
   } else {
-    // chunk q = [q * cs, min((q + 1) * cs, n4)) in float4 units
     const int64_t cs = (n4 + c.world - 1) / c.world;
-    if (PHASE == 1) {
-      const int64_t lo = (int64_t)c.rank * cs, hi = (lo + cs < n4) ? lo + cs : n4;
-      for (int64_t i = lo + tid; i < hi; i += stride) {
-        float4 acc = ld_peer_f4(c.buf[0] + 4 * i);
-        for (int q = 1; q < c.world; ++q) {
-          const float4 v = ld_peer_f4(c.buf[q] + 4 * i);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        reinterpret_cast<float4*>(c.buf[c.rank])[i] = acc;
+    for (int64_t i0 = tid; i0 < n4; i0 += U * stride) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        v[u] = (i < n4) ? ld_peer_f4(c.buf[(int)(i / cs)] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (tid == 0) comm_reduce_tail(c, npad, g + npad);
-    } else {
-      for (int64_t i = tid; i < n4; i += stride) {
-        int q = (int)(i / cs);
-        reinterpret_cast<float4*>(g)[i] = ld_peer_f4(c.buf[q] + 4 * i);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < n4) reinterpret_cast<float4*>(g)[i] = v[u];
       }
     }
   }

@@ -116,6 +116,7 @@ struct TileArgs {
   int rb;
   int x_vec_ok;  // X 16-byte aligned: the dst tile comes by cp.async.bulk
   int g_vec_ok;  // grad 16-byte aligned: the gradient tile is flushed with red.v4
+  int gred;      // 1: dst contributions leave as global reds (no gradient tile, no CAS); the X tile may be twice as large
 };
 
 // PushAndPull(Log1p(1.5), Log(1.0)) with MUFU math (mde_common.cuh::edge_coeff_fast_log1p_log), one-sided when the
@@ -187,7 +188,16 @@ __device__ __forceinline__ void quad_compute(const TileArgs& a, const float* __r
       float v[M];
 #pragma unroll
       for (int cc = 0; cc < M; ++cc) v[cc] = live ? g * diff[cc] : 0.0f;
-      if (live) smem_sub_row<M>(Gt, dl[e], v);
+      if (live) {
+        if (a.gred) {
+          float nv[M];
+#pragma unroll
+          for (int cc = 0; cc < M; ++cc) nv[cc] = -v[cc];
+          red_row_g<M>(a.grad, td[e], nv);
+        } else {
+          smem_sub_row<M>(Gt, dl[e], v);
+        }
+      }
       const int se = ok ? s[e] : cur;  // pads never break a run
       if (se != cur) {                 // run of equal src ended: flush its sum
         red_row_g<M>(a.grad, cur, acc);
@@ -213,8 +223,8 @@ distortion_tile_kernel(const TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int R = 1 << a.rb;
   float* Xt = reinterpret_cast<float*>(smem_raw);
-  float* Gt = Xt + R * M;
-  unsigned char* slots = reinterpret_cast<unsigned char*>(Gt + R * M);
+  float* Gt = Xt + R * M;  // (unused when a.gred)
+  unsigned char* slots = reinterpret_cast<unsigned char*>(Xt + (a.gred ? 1 : 2) * R * M);
   uint64_t* bars = reinterpret_cast<uint64_t*>(slots + kTileWarps * kWtBytes);
   double* red = reinterpret_cast<double*>(bars + kTileWarps + 2);
 
@@ -252,7 +262,7 @@ distortion_tile_kernel(const TileArgs a) {
     seg_end = be < wt1 ? be : wt1;
     if (new_tile == tile) return;  // same dst tile, other src super-tile: keep accumulating
     __syncthreads();               // every warp is done with the old tile
-    if (!first && MODE != 1) {
+    if (!first && MODE != 1 && !a.gred) {
       // flush: grad[tile rows] += Gt, zero Gt (same thread reads and clears an element)
       const int64_t rows_l = a.n - base;
       const int rows = (int)(rows_l < (int64_t)R ? rows_l : (int64_t)R);
@@ -284,7 +294,7 @@ distortion_tile_kernel(const TileArgs a) {
     const int rows = (int)(rows_l < (int64_t)R ? rows_l : (int64_t)R);
     const int nfl = rows * M;
     const float* xsrc = a.X + base * M;
-    if (first && MODE != 1) {
+    if (first && MODE != 1 && !a.gred) {
       float4* G4 = reinterpret_cast<float4*>(Gt);
       for (int i = threadIdx.x; i < ((R * M) >> 2); i += kTileThreads) G4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -322,9 +332,13 @@ distortion_tile_kernel(const TileArgs a) {
       asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(t4.x), "=r"(t4.y), "=r"(t4.z), "=r"(t4.w) : "r"(q + 512u));
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(q + 1024u));
     }
-    __syncwarp();
+    // WAR on the slot: the next record may only be requested once EVERY lane's loads have returned (a lane issues
+    // the ballot after consuming one element of each vector load; the result feeds a never-taken branch)
+    {
+      const unsigned chk = (unsigned)(s4.w ^ t4.w) ^ __float_as_uint(a4.w);
+      if (__ballot_sync(kFull, chk == 0x7fc12345u) == 0x80000001u) lsum += 1e-300;
+    }
     if (lane == 0 && t + kTileWarps < wt1) {  // refill the slot: the record is in registers now
-      fence_proxy_async();
       mbar_expect_tx(my_bar, kWtBytes);
       bulk_g2s_hint(my_slot, a.rec + (int64_t)(t + kTileWarps) * kWtWords, kWtBytes, my_bar, pol);
     }
@@ -360,7 +374,7 @@ distortion_tile_kernel(const TileArgs a) {
   if (first && wt0 < wt1) { enter_bucket(true); first = false; }
   while (seg_end < wt1) { ++bkt; enter_bucket(false); }
   __syncthreads();
-  if (MODE != 1 && tile >= 0) {  // final flush
+  if (MODE != 1 && tile >= 0 && !a.gred) {  // final flush
     const int64_t rows_l = a.n - base;
     const int rows = (int)(rows_l < (int64_t)R ? rows_l : (int64_t)R);
     const int nfl = rows * M;
@@ -476,8 +490,8 @@ int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-size_t tile_smem_bytes(int rb, int m) {
-  return (size_t)2 * ((size_t)1 << rb) * m * sizeof(float) + (size_t)kTileWarps * kWtBytes +
+size_t tile_smem_bytes(int rb, int m, int gred) {
+  return (size_t)(gred ? 1 : 2) * ((size_t)1 << rb) * m * sizeof(float) + (size_t)kTileWarps * kWtBytes +
          (size_t)(kTileWarps + 2) * sizeof(uint64_t) + 32 * sizeof(double);
 }
 
@@ -498,8 +512,10 @@ int tiled_build(mde_edges* e, const int64_t* edges, const float* par0, const mde
   const int64_t p = e->p, n = e->n;
   if (m < 1 || m > 4) return MDE_E_UNSUPPORTED;
   int rb = (m <= 2) ? 13 : 12;  // R = 8192 rows (m <= 2) / 4096 rows: X tile + gradient tile = 128 KB
-  { const int r = env_int("MDE_B200_TILE_RB", 0); if (r >= 8 && r <= 14) rb = r; }
-  if (tile_smem_bytes(rb, m) > 227u * 1024u) return MDE_E_UNSUPPORTED;
+  { const int r = env_int("MDE_B200_TILE_RB", 0); if (r >= 8 && r <= 15) rb = r; }
+  int gred = 0;
+  { const char* ev = getenv("MDE_B200_TILE_SCATTER"); if (ev && !strcmp(ev, "global")) gred = 1; }
+  if (tile_smem_bytes(rb, m, gred) > 227u * 1024u) return MDE_E_UNSUPPORTED;
   // src super-tile: X + gradient rows of one super-tile (2 * m * 4 bytes per row) stay L2-resident
   int64_t l2_bytes = (int64_t)env_int("MDE_B200_STILE_MB", 48) << 20;
   int ss = rb;
@@ -601,6 +617,7 @@ int tiled_build(mde_edges* e, const int64_t* edges, const float* par0, const mde
     TRY(cudaStreamSynchronize(st));
     e->fn = to_dev(*fn);
     if ((rc = tiled_configure(e, m))) goto done;
+    e->gred = gred;
     e->kind = 1; e->m_hint = m; e->rb = rb; e->ss = ss; e->nwt = nwt; e->nbkt = nbkt; e->ncta = ncta;
     e->nbytes = nwt * (kWtBytes + 4 * kWtEdges) + 8 * kMaxLossBlocks + 4ll * (2 * nbkt + 2 * ncta + 2);
   }
@@ -680,7 +697,7 @@ int tiled_configure(const mde_edges* e, int m) {
 int tiled_launch(int mode, const mde_edges* e, const float* X, int m, float* grad, const float* gext,
                  int* nblocks_out, const int* flag, cudaStream_t st) {
   if (e->kind != 1 || m < 1 || m > 4) return MDE_E_UNSUPPORTED;
-  const size_t smem = tile_smem_bytes(e->rb, m);
+  const size_t smem = tile_smem_bytes(e->rb, m, e->gred);
   if (smem > 227u * 1024u) return MDE_E_UNSUPPORTED;  // layout built for a smaller embedding dimension
   TileArgs a;
   a.rec = e->rec; a.perm = e->perm; a.gext = gext; a.bkt_tile = e->bkt_tile; a.bkt_wt0 = e->bkt_wt0;
@@ -688,6 +705,7 @@ int tiled_launch(int mode, const mde_edges* e, const float* X, int m, float* gra
   a.flag = flag; a.fn = e->fn; a.inv_p = 1.0f / (float)e->p_total; a.n = e->n; a.rb = e->rb;
   a.x_vec_ok = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) ? 1 : 0;
   a.g_vec_ok = ((reinterpret_cast<uintptr_t>(grad) & 15u) == 0) ? 1 : 0;
+  a.gred = e->gred;
   const void* k = select_kernel(e->fn, m, mode);
   if (!k) return MDE_E_UNSUPPORTED;
   int rc = configure_kernel(k);

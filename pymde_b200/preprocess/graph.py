@@ -117,6 +117,68 @@ class Graph(object):
         raise AttributeError("Graph objects are immutable.")
 
 
+class EdgeListGraph(object):
+    """Result of the device shortest-path search: an edge list that never left the GPU.  Quacks like the part of
+    `Graph` the recipes use (`edges` sorted by (i, j), `distances`, `n_items`); `to_graph()` builds the scipy-backed
+    object when somebody needs the adjacency matrix."""
+
+    def __init__(self, edges, distances, n_items):
+        self.edges, self.distances, self._n = edges, distances, int(n_items)
+        self.weights = distances
+
+    @property
+    def n_items(self):
+        return self._n
+
+    @property
+    def n_edges(self):
+        return int(self.edges.shape[0])
+
+    @property
+    def n_all_edges(self):
+        return self._n * (self._n - 1) // 2
+
+    def to_graph(self):
+        return Graph.from_edges(self.edges.cpu().numpy(), self.distances.cpu().numpy(), n_items=self._n)
+
+
+def shortest_paths_device(graph, max_length=None, retain_fraction=1.0, device=None, seed=None):
+    """Hop-count shortest paths of an UNWEIGHTED graph on the GPU (`mde_graph_hops`: bit-parallel multi-source BFS,
+    256 sources per pass over the adjacency).  Same contract as `shortest_paths` -- pairs (i < j) within `max_length`
+    hops, each kept with probability `retain_fraction` -- but the sample is drawn by a counter-based hash seeded from
+    the module RNG, and the result stays on the device as an `EdgeListGraph`."""
+    import ctypes as C
+    from .. import _lib, util
+    A = graph.adjacency_matrix if isinstance(graph, Graph) else Graph(graph).adjacency_matrix
+    n = A.shape[0]
+    dev = util.cuda_device(device)
+    lib = _lib.load()
+    indptr = torch.tensor(A.indptr.astype(np.int32), device=dev)
+    indices = torch.tensor(A.indices.astype(np.int32), device=dev)
+    ws = torch.empty(int(lib.mde_graph_hops_ws_bytes(n)), dtype=torch.uint8, device=dev)
+    if seed is None:
+        seed = int(util.np_rng().integers(0, 2 ** 62))
+    expected = min(1.0, float(retain_fraction)) * n * (n - 1) / 2
+    cap = int(expected * 1.02 + 4 * (expected ** 0.5) + 1024)
+    limit = 0 if (max_length is None or not np.isfinite(max_length)) else int(max_length)
+    while True:
+        src = torch.empty(cap, dtype=torch.int32, device=dev)
+        dst = torch.empty(cap, dtype=torch.int32, device=dev)
+        ln = torch.empty(cap, dtype=torch.float32, device=dev)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mde_graph_hops(indptr.data_ptr(), indices.data_ptr(), n, 0, n, limit, float(retain_fraction),
+                                          C.c_uint64(seed), src.data_ptr(), dst.data_ptr(), ln.data_ptr(), cap,
+                                          count.data_ptr(), ws.data_ptr(), ws.numel(), util.stream_ptr(dev)))
+        got = int(count.item())
+        if got <= cap:
+            break
+        cap = int(got * 1.01) + 1024  # (only when the estimate was exceeded: same seed => same sample)
+    src, dst, ln = src[:got].long(), dst[:got].long(), ln[:got]
+    order = torch.argsort(src * n + dst)
+    return EdgeListGraph(torch.stack([src[order], dst[order]], 1), ln[order], n)
+
+
 def shortest_paths(graph, max_length=None, retain_fraction=1.0, n_workers=None, verbose=False):
     """Shortest-path distances as a Graph (interface of pymde/preprocess/graph.py:345-474): unreachable pairs and
     pairs beyond `max_length` are dropped; with `retain_fraction` < 1 every remaining pair is kept with that

@@ -80,12 +80,12 @@ X2 = pm.Standardized().initialization(n2, 2, dev) if False else None
 Xi = torch.randn(n2, 2, generator=gen).to(dev)
 Xi = pm.Standardized().project_onto_constraint(Xi, inplace=True)
 ms = pdist.shard_mde(pm.MDE, n2, 2, e2t, mk2, pm.Standardized(), dev, transport="peer")
-ms.embed(X=Xi, max_iter=400, eps=1e-6)
+ms.embed(X=Xi, max_iter=800, eps=1e-5)
 conv = {"iterations": ms.solve_stats.iterations, "value": float(ms.solve_stats.average_distortions[-1]),
         "residual": float(ms.solve_stats.residual_norms[-1]), "x_identical": digests_equal(ms.X)}
 if rank == 0:
     one = pm.MDE(n2, 2, e2t.to(dev), mk2(0, p2), pm.Standardized(), device=dev)
-    one.embed(X=Xi, max_iter=400, eps=1e-6)
+    one.embed(X=Xi, max_iter=800, eps=1e-5)
     conv["single_value"] = float(one.solve_stats.average_distortions[-1])
     conv["single_iterations"] = one.solve_stats.iterations
     conv["rel"] = abs(conv["value"] - conv["single_value"]) / abs(conv["single_value"])

@@ -90,7 +90,10 @@ def test_c2slice_converged_value_within_the_references_own_spread(c2slice):
     spread = refs.max() - refs.min()
     assert spread > 1e-5 * refs.mean()  # (documents why a 1e-5 comparison of end points is not defined here)
     final = mde.average_distortion(X).item()
-    assert refs.min() - 2 * spread <= final <= refs.max() + 2 * spread, (final, refs)
+    # not worse than the reference's own worst run (it may be better: 0.1511 against 0.1520-0.1530 on B200), and the
+    # same basin: within 2 % of the reference's best
+    assert final <= refs.max() + 2 * spread, (final, refs)
+    assert final >= 0.98 * refs.min(), (final, refs)
 
 
 def test_c2slice_300_iterations_centered(c2slice):
@@ -103,7 +106,7 @@ def test_c2slice_300_iterations_centered(c2slice):
     assert len(a) == 300
     np.testing.assert_allclose(a[0], r8[0], rtol=1e-5)
     np.testing.assert_allclose(mde.solve_stats.residual_norms[0], g["cen/t8/residual_norms"][0], rtol=1e-4)
-    _inside_reference_envelope(a, [r8, r1], 6)
+    _inside_reference_envelope(a, [r8, r1], 4)  # (from iteration 4 on the two reference runs cross each other)
     # after 300 iterations the reference's two runs differ by several percent; ours must be as good a descent
     lo, hi = min(r8[-1], r1[-1]), max(r8[-1], r1[-1])
     assert a[-1] <= hi + 2 * (hi - lo), (a[-1], lo, hi)

@@ -12,6 +12,18 @@ from tests.golden_cases import CASES, spec_for
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["auto", "soa", "tiles", "pull"], autouse=True)
+def edge_layout(request, monkeypatch):
+    """Every test of this file runs on each edge layout / kernel family: the library's own choice, the sorted-SoA
+    layout (quad / strided / wide kernels), tile records (push kernel) and pull records (mde_edges.cuh).  Layouts that
+    do not apply (m > 4, WeightedQuadratic's second array) fall back to SoA inside the library."""
+    if request.param != "auto":
+        monkeypatch.setenv("MDE_B200_LAYOUT", request.param)
+    else:
+        monkeypatch.delenv("MDE_B200_LAYOUT", raising=False)
+    return request.param
+
+
 def _pm():
     import pymde_b200 as pm
     return pm
@@ -307,16 +319,13 @@ def test_full_size_c2_against_c_oracle():
 
 
 @pytest.mark.parametrize("kernel", ["fast", "precise"])
-@pytest.mark.parametrize("layout", [None, "soa", "tiles"])
 @pytest.mark.parametrize("m", [2, 3])
-def test_near_zero_distances_match_reference(golden, m, layout, kernel, monkeypatch):
+def test_near_zero_distances_match_reference(golden, m, kernel, monkeypatch):
     """Edges between near-duplicate points (1e-6 <= d <= 1e-1) and exact duplicates (d = 0), attractive and
     repulsive: the MUFU kernels' small-d series for 1 - exp(-d) and the d = 0 mask against the reference's fp64
     run.  The reference's VALUE is -inf when a repulsive edge has d = 0 (log(0)); its gradient is still defined
     (non-finite coefficient -> 1, zero difference vector), so the value is compared on the edges with d > 0."""
     pm = _pm()
-    if layout:
-        monkeypatch.setenv("MDE_B200_LAYOUT", layout)
     if kernel == "precise":
         monkeypatch.setenv("MDE_B200_KERNEL", "precise")
     g = golden["nearzero"]

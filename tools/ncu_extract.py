@@ -23,8 +23,12 @@ def to_bytes(value, unit):
 
 def main():
     rep, key, raw_out = sys.argv[1], sys.argv[2], sys.argv[3]
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    open(raw_out, "w").write(txt)
+    if rep.endswith(".csv"):  # an already exported raw page (e.g. the r01 captures whose .ncu-rep was not kept)
+        txt = open(rep).read()
+        raw_out = rep
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        open(raw_out, "w").write(txt)
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     col = {h: i for i, h in enumerate(hdr)}
