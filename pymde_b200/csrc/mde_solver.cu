@@ -692,9 +692,11 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// peer rows are read with ld.global.cg: never served from a (possibly stale) L1 line, and -- unlike a volatile
-// load -- free to be batched, so a thread keeps several NVLink requests in flight
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+// Peer rows are read with plain (L1-allocating) 16-byte loads: a warp's 512 contiguous bytes travel as whole
+// 128-byte lines over NVLink.  (ld.global.cg sustained only ~300 GB/s here: peer data is never cached in the local L2,
+// so .cg requests go out sector by sector.)  Stale L1 lines cannot be hit: L1 is invalidated at every kernel launch
+// and an address is read at most once per launch, after the acquire of its owner's flag.
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // tell every rank "my epoch for this flag kind is `v`" (threads 0..W-1 of one block)
 __device__ __forceinline__ void comm_signal(unsigned* const* flags, const Comm& c, unsigned v) {
@@ -744,7 +746,7 @@ allreduce_kernel(const int* __restrict__ flag, Comm c, float* __restrict__ g, in
   const int64_t n4 = npad >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  constexpr int U = 4;  // float4 per thread per trip: U * world independent 16-byte loads in flight
+  constexpr int U = 2;  // float4 per thread per trip; all U * world peer loads are issued before the first add
   if (PHASE == 0 || PHASE == 1) {
     // chunk q = [q * cs, min((q + 1) * cs, n4)) in float4 units; one-shot reduces everything, reduce-scatter its chunk
     const int64_t cs = (n4 + c.world - 1) / c.world;
@@ -752,40 +754,39 @@ allreduce_kernel(const int* __restrict__ flag, Comm c, float* __restrict__ g, in
     const int64_t hi = (PHASE == 0) ? n4 : ((lo + cs < n4) ? lo + cs : n4);
     float* out = (PHASE == 0) ? g : c.buf[c.rank];
     for (int64_t i0 = lo + tid; i0 < hi; i0 += U * stride) {
-      float4 acc[U];
+      float4 v[kMaxWorld][U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t i = i0 + u * stride;
-        acc[u] = (i < hi) ? ld_peer_f4(c.buf[0] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      for (int q = 1; q < c.world; ++q) {  // rank order: bit-identical sums on every rank
-        float4 v[U];
+      for (int q = 0; q < kMaxWorld; ++q) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int64_t i = i0 + u * stride;
-          v[u] = (i < hi) ? ld_peer_f4(c.buf[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[q][u] = (q < c.world && i < hi) ? ld_peer_f4(c.buf[q] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        float4 acc = v[0][u];
+#pragma unroll
+        for (int q = 1; q < kMaxWorld; ++q) {  // rank order: bit-identical sums on every rank (absent ranks add +0)
+          if (q < c.world) { acc.x += v[q][u].x; acc.y += v[q][u].y; acc.z += v[q][u].z; acc.w += v[q][u].w; }
+        }
         const int64_t i = i0 + u * stride;
-        if (i < hi) reinterpret_cast<float4*>(out)[i] = acc[u];
+        if (i < hi) reinterpret_cast<float4*>(out)[i] = acc;
       }
     }
     if (tid == 0) comm_reduce_tail(c, npad, g + npad);
   } else {
     const int64_t cs = (n4 + c.world - 1) / c.world;
-    for (int64_t i0 = tid; i0 < n4; i0 += U * stride) {
-      float4 v[U];
+    constexpr int UG = 8;
+    for (int64_t i0 = tid; i0 < n4; i0 += UG * stride) {
+      float4 v[UG];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < UG; ++u) {
         const int64_t i = i0 + u * stride;
         v[u] = (i < n4) ? ld_peer_f4(c.buf[(int)(i / cs)] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < UG; ++u) {
         const int64_t i = i0 + u * stride;
         if (i < n4) reinterpret_cast<float4*>(g)[i] = v[u];
       }
@@ -1242,7 +1243,7 @@ int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cud
     if (s->comm_connected) {
       const int64_t n4 = s->npad >> 2;
       int nb = (int)((n4 + kCommThreads - 1) / kCommThreads);
-      if (nb > kNumSMs * 2) nb = kNumSMs * 2;
+      if (nb > kNumSMs) nb = kNumSMs;  // one resident 512-thread block per SM (84-100 registers): a single wave
       if (nb < 1) nb = 1;
       if ((s->npad + 4) * (int64_t)sizeof(float) <= kOneShotBytes) {
         allreduce_kernel<0><<<nb, kCommThreads, 0, st>>>(flag, s->comm, s->g, s->npad, &s->S->error);
