@@ -40,6 +40,12 @@ def test_two_rank_sharded_evaluation_and_solve():
         assert t["loss0_rel"] < 1e-5 and t["resid0_rel"] < 1e-4
         assert t["first3_rel_vs_single"] < 1e-3
     assert r["peer"]["peer_memory"] and not r["nccl"]["peer_memory"]
+    # (iv) gradient above the one-shot limit: write-based and read-based two-shot all-reduce
+    for mode in ("push", "pull"):
+        t = r["big"][mode]
+        assert t["iterations"] == 8 and t["x_identical"] and t["decreased"]
+        assert t["loss0_rel"] < 1e-5 and t["resid0_rel"] < 1e-4
+        assert t["first3_rel_vs_single"] < 1e-3
     # (iii) converged problem: the north_star's criterion
     c = r["converged"]
     assert c["x_identical"] and c["iterations"] < 800 and c["single_iterations"] < 800
