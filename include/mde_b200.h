@@ -102,6 +102,11 @@ int64_t mde_edges_count(const mde_edges_t* e);
  * (push kernel, shared-memory dst tile), 2 = pull records (directed entries, no shared-memory atomics).
  * MDE_B200_LAYOUT=soa|tiles|pull overrides the choice (A/B measurements). */
 int mde_edges_kind(const mde_edges_t* e);
+/* 1 when the layout was created with MDE_B200_DETERMINISTIC=1 (embedding_dim <= 4): gradient contributions are
+ * accumulated as 64-bit fixed point (2^-40 resolution), so value AND gradient are bit-reproducible run to run and
+ * independent of the scheduling of the reds -- the reference's scatter_add_ is not (pymde/average_distortion.py:75-76).
+ * Costs two 64-bit reds per row update instead of one vector red. */
+int mde_edges_deterministic(const mde_edges_t* e);
 /* bytes of device memory held by the layout */
 int64_t mde_edges_nbytes(const mde_edges_t* e);
 

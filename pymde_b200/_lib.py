@@ -48,6 +48,7 @@ SIGNATURES = {
     "mde_edges_count": (C.c_int64, [C.c_void_p]),
     "mde_edges_nbytes": (C.c_int64, [C.c_void_p]),
     "mde_edges_kind": (C.c_int, [C.c_void_p]),
+    "mde_edges_deterministic": (C.c_int, [C.c_void_p]),
     "mde_distortion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mde_edge_outputs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mde_function_eval": (C.c_int, [C.POINTER(mde_fn_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,

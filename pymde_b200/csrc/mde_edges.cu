@@ -85,6 +85,32 @@ __device__ __forceinline__ Row<M> load_row(const float* __restrict__ X, int r) {
   return o;
 }
 
+// Deterministic mode: contributions are accumulated as 64-bit fixed point (scale 2^40, resolution 9e-13, range
+// +-8.4e6 -- the entries are f'/p-sized).  Integer addition is associative, so the sums do not depend on the order in
+// which the reds land (the float reds of the default mode, like the reference's scatter_add_, do:
+// pymde/average_distortion.py:75-76).
+constexpr float kFxScale = 1099511627776.0f;  // 2^40
+template <int M>
+__device__ __forceinline__ void red_row_fx(long long* __restrict__ F, int r, const float (&v)[M], float sgn) {
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    const long long q = __float2ll_rn(sgn * v[c] * kFxScale);
+    atomicAdd(reinterpret_cast<unsigned long long*>(F + (int64_t)r * M + c), (unsigned long long)q);
+  }
+}
+__global__ void fx_zero_kernel(const int* __restrict__ flag, long long* __restrict__ F, int64_t count) {
+  if (flag != nullptr && *flag == 0) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) F[i] = 0ll;
+}
+__global__ void fx_apply_kernel(const int* __restrict__ flag, const long long* __restrict__ F, float* __restrict__ grad,
+                                int64_t count) {
+  if (flag != nullptr && *flag == 0) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    grad[i] += (float)((double)F[i] * (1.0 / 1099511627776.0));
+}
+
 template <int M>
 __device__ __forceinline__ void red_row(float* __restrict__ G, int r, const float (&v)[M], float sgn) {
   if constexpr (M == 1) red_add(G + r, sgn * v[0]);
@@ -197,7 +223,7 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
                        const int32_t* __restrict__ perm, const float* __restrict__ gext,
                        int64_t p, const float* __restrict__ X, float* __restrict__ grad,
                        double* __restrict__ loss_partials, FnDev fn, float inv_p,
-                       const int* __restrict__ flag) {
+                       const int* __restrict__ flag, long long* __restrict__ fx) {
   if (flag != nullptr && *flag == 0) return;
   constexpr int E = 4 * NQ;  // consecutive edges owned by a thread per iteration
   const int64_t nquads = (p + 3) >> 2;
@@ -290,9 +316,9 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
         float v[M];
 #pragma unroll
         for (int c = 0; c < M; ++c) v[c] = live ? g * diff[c] : 0.0f;
-        if (live) red_row<M>(grad, t[e], v, -1.0f);
+        if (live) { if (fx) red_row_fx<M>(fx, t[e], v, -1.0f); else red_row<M>(grad, t[e], v, -1.0f); }
         if (s[e] != cur) {  // run of equal src ended: flush its sum
-          red_row<M>(grad, cur, acc, 1.0f);
+          if (fx) red_row_fx<M>(fx, cur, acc, 1.0f); else red_row<M>(grad, cur, acc, 1.0f);
           cur = s[e];
 #pragma unroll
           for (int c = 0; c < M; ++c) acc[c] = 0.0f;
@@ -301,7 +327,7 @@ distortion_quad_kernel(const int32_t* __restrict__ src, const int32_t* __restric
         for (int c = 0; c < M; ++c) acc[c] += v[c];
       }
     }
-    if (MODE != 1) red_row<M>(grad, cur, acc, 1.0f);
+    if (MODE != 1) { if (fx) red_row_fx<M>(fx, cur, acc, 1.0f); else red_row<M>(grad, cur, acc, 1.0f); }
     if (FAST) { lsum += (double)lsum_f; lsum_f = 0.0f; }
   }
   if (MODE != 2) {
@@ -546,6 +572,15 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
   const float inv_p = 1.0f / (float)e->p_total;
   const int64_t p = e->p;
   int nb;
+  // deterministic mode (m <= 4, sorted-SoA layout): zero the fixed-point buffer, accumulate into it, add it to grad
+  long long* fxp = nullptr;
+  if (e->det && MODE != 1 && m <= 4 && m <= e->m_hint && small_kernel_variant() != 1) {
+    fxp = e->fx;
+    const int64_t cnt = e->n * m;
+    int zb = (int)((cnt + 255) / 256); if (zb > kNumSMs * 8) zb = kNumSMs * 8;
+    fx_zero_kernel<<<zb, 256, 0, st>>>(flag, fxp, cnt);
+    ++g_launch_count;
+  }
 #define SMALLK(MM, FA, FR)                                                                            \
   distortion_small_kernel<MM, MODE, FA, FR><<<nb, kSmallThreads, 0, st>>>(                            \
       e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
@@ -554,7 +589,7 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
 #define QUADK_(MM, FA, FR, FAST, NQV)                                                                 \
   distortion_quad_kernel<MM, MODE, FA, FR, FAST, NQV><<<nb, kQuadThreads, 0, st>>>(                   \
       e->src, e->dst, e->par0, e->has_par1 ? e->par1 : nullptr, e->perm, gext, p, X, grad,           \
-      e->loss_partials, e->fn, inv_p, flag)
+      e->loss_partials, e->fn, inv_p, flag, fxp)
 #define QUADK(MM, FA, FR, FAST)                                                                       \
   if (FAST && quad_nq() == 2) { nb = loss_blocks_quad(p, 2); QUADK_(MM, FA, FR, FAST, 2); }           \
   else { nb = loss_blocks_quad(p, 1); QUADK_(MM, FA, FR, FAST, 1); }
@@ -627,6 +662,12 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
 #undef SMALLK
 #undef WIDE
   MDE_LAUNCH_CHECK();
+  if (fxp) {
+    const int64_t cnt = e->n * m;
+    int zb = (int)((cnt + 255) / 256); if (zb > kNumSMs * 8) zb = kNumSMs * 8;
+    fx_apply_kernel<<<zb, 256, 0, st>>>(flag, fxp, grad, cnt);
+    MDE_LAUNCH_CHECK();
+  }
   if (nblocks_out) *nblocks_out = nb;
   return 0;
 }
@@ -710,13 +751,20 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
   // faster, and needs half the layout memory.
   dense = (p / n_items) >= 64;
   pref = layout_pref();
+  {  // MDE_B200_DETERMINISTIC=1: order-independent (fixed-point) gradient accumulation; sorted-SoA layout, m <= 4
+    const char* ev = getenv("MDE_B200_DETERMINISTIC");
+    if (ev && ev[0] == '1' && embedding_dim >= 1 && embedding_dim <= 4) {
+      e->det = 1; e->m_hint = embedding_dim; pref = 1;
+      TRY(cudaMalloc(&e->fx, sizeof(long long) * n_items * embedding_dim));
+    }
+  }
   if (embedding_dim >= 1 && embedding_dim <= 4 && !par1 && pref != 1 && (pref != 0 || dense)) {
-    if (layout_pref() != 2) {  // pull records
+    if (pref != 2) {  // pull records
       rc = pull_build(e, edges, par0, fn, embedding_dim, st);
       if (rc == 0) { *out = e; return 0; }
       if (rc != MDE_E_UNSUPPORTED) goto fail;
     }
-    if (layout_pref() != 3) {
+    if (pref != 3) {
       rc = tiled_build(e, edges, par0, fn, embedding_dim, st);
       if (rc == 0) { *out = e; return 0; }
       if (rc != MDE_E_UNSUPPORTED) goto fail;
@@ -761,7 +809,7 @@ fail:
 int mde_edges_destroy(mde_edges_t* e) {
   if (!e) return 0;
   cudaFree(e->src); cudaFree(e->dst); cudaFree(e->perm); cudaFree(e->par0); cudaFree(e->par1);
-  cudaFree(e->loss_partials);
+  cudaFree(e->loss_partials); cudaFree(e->fx);
   tiled_free(e);
   pull_free(e);
   delete e;
@@ -770,6 +818,7 @@ int mde_edges_destroy(mde_edges_t* e) {
 
 int64_t mde_edges_count(const mde_edges_t* e) { return e ? e->p : 0; }
 int mde_edges_kind(const mde_edges_t* e) { return e ? e->kind : -1; }
+int mde_edges_deterministic(const mde_edges_t* e) { return e ? e->det : 0; }
 int64_t mde_edges_nbytes(const mde_edges_t* e) { return e ? e->nbytes : 0; }
 
 int mde_distortion(const mde_edges_t* e, const float* X, int m, float* grad, double* loss_sum,

@@ -34,6 +34,8 @@ struct mde_edges {
   mde::FnDev fn;
   int has_par1 = 0;
   int64_t nbytes = 0;
+  int det = 0;               // deterministic mode: gradient contributions accumulate in 64-bit fixed point
+  long long* fx = nullptr;   // [n * m_hint] fixed-point accumulator (det only)
   // ---- kind 1 ----
   int m_hint = 0;          // embedding dimension the tile size was chosen for
   int rb = 0;              // log2(R): dst tile rows

@@ -107,3 +107,49 @@ def test_external_coefficients_edge_count_not_multiple_of_4(layout, extra, monke
     ref.backward()
     np.testing.assert_allclose(v.item(), ref.item(), rtol=1e-5)
     np.testing.assert_allclose(Xd.grad.cpu().numpy(), Xr.grad.cpu().numpy(), atol=2e-5 * float(Xr.grad.abs().max()))
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_deterministic_mode_is_bit_reproducible(m, monkeypatch):
+    """MDE_B200_DETERMINISTIC=1: 64-bit fixed-point accumulation of the gradient contributions (integer adds are
+    associative), fixed-order loss sums => value, gradient and whole embed() trajectories are bit-identical run to run.
+    The reference's scatter_add_ on CUDA is not (pymde/average_distortion.py:75-76)."""
+    import pymde_b200 as pm
+    from pymde_b200 import _lib
+    from oracle import mde_oracle as O
+    dev = torch.device("cuda", 0)
+    monkeypatch.setenv("MDE_B200_DETERMINISTIC", "1")
+    rng = np.random.default_rng(10 + m)
+    n, p = 3000, 60000
+    e = rng.integers(0, n, (2 * p, 2))
+    e = np.unique(np.sort(e[e[:, 0] != e[:, 1]], axis=1), axis=0)[:p]
+    w = rng.choice([1.0, 2.0, -1.0], len(e)).astype(np.float32)
+    X0 = rng.standard_normal((n, m)).astype(np.float32)
+    X0 -= X0.mean(0)
+
+    def problem():
+        f = pm.penalties.PushAndPull(torch.tensor(w, device=dev), pm.penalties.Log1p, pm.penalties.Log)
+        return pm.MDE(n, m, torch.tensor(e, device=dev), f, pm.Centered(), device=dev)
+
+    grads, values = [], []
+    for _ in range(3):
+        mde = problem()
+        assert _lib.load().mde_edges_deterministic(mde._layout().handle) == 1
+        X = torch.tensor(X0, device=dev, requires_grad=True)
+        v = mde.average_distortion(X)
+        v.backward()
+        grads.append(X.grad.clone())
+        values.append(v.item())
+    assert values[0] == values[1] == values[2]
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    spec = O.FnSpec(O.P_LOG1P, w, (1.5, 0, 0), fn_rep=O.P_LOG, rep=(1.0, 0, 0))
+    v_ref, g_ref = O.average_distortion(X0.astype(np.float64), e, spec, True)
+    np.testing.assert_allclose(values[0], v_ref, rtol=1e-5)
+    np.testing.assert_allclose(grads[0].cpu().numpy(), g_ref, atol=3e-5 * np.abs(g_ref).max())
+    runs = []
+    for _ in range(2):
+        mde = problem()
+        runs.append((mde.embed(X=torch.tensor(X0, device=dev), max_iter=40, eps=0.0).clone(),
+                     list(mde.solve_stats.average_distortions)))
+    assert torch.equal(runs[0][0], runs[1][0])
+    assert runs[0][1] == runs[1][1]
