@@ -431,13 +431,13 @@ def ours_single(args, K, W, torch, pm, _lib, lib, dev, barrier):
                          "rel_diff_last": abs(ours_traj[k_cmp - 1] - rt[k_cmp - 1]) / abs(rt[k_cmp - 1])}
 
     ips = K / (ms * 1e-3)
-    cfg = make_config(1)
-    cfg.update({"edges_total": p, "edges_per_gpu": p, "repeats": REPEATS})
+    cfg = make_config(1)  # identical in both arms (the driver compares it); run details go to top-level keys
     line = {
         "metric": "embed_edges_per_sec", "value": ips * p, "unit": "edges/s", "n_gpus": 1, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "iters_per_sec": ips, "timed_windows_ms": windows, "func_evals_total": int(fe),
+        "edges_total": p, "edges_per_gpu": p, "repeats": REPEATS,
         "average_distortion_after_%d_iterations" % done: float(avg[-1]) if len(avg) else None,
         "e2e": {"value": e2e_iters / e2e_s * p, "unit": "edges/s", "iters_per_sec": e2e_iters / e2e_s,
                 "h2d_bytes_per_step": h2d / max(e2e_iters, 1), "d2h_bytes_per_step": d2h / max(e2e_iters, 1),
@@ -566,14 +566,14 @@ def ours_sharded(args, K, W, rank, world, torch, tdist, pm, pdist, _lib, lib, de
     if rank != 0:
         return 0
     ips = K / (ms * 1e-3)
-    cfg = make_config(world)
-    cfg.update({"edges_total": p_total, "edges_per_gpu": p_local, "repeats": REPEATS,
-                "allreduce": "peer-memory kernels (cudaIpc + flag handshake, graph-captured)" if peer else "NCCL host hook"})
+    cfg = make_config(world)  # identical in both arms (the driver compares it); run details go to top-level keys
     line = {
         "metric": "embed_edges_per_sec", "value": ips * p_total, "unit": "edges/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "iters_per_sec": ips, "timed_windows_ms": windows, "func_evals_total": int(fe),
+        "edges_total": p_total, "edges_per_gpu": p_local, "repeats": REPEATS,
+        "allreduce": "peer-memory kernels (cudaIpc + flag handshake, graph-captured)" if peer else "NCCL host hook",
         "single_gpu": {"what": "rank-local shard (%d edges, n=%d) solved alone on one GPU, max over ranks" % (p_local, n),
                        "ms_per_step": solo_ms, "value": p_local / (solo_ms * 1e-3), "unit": "edges/s"},
         "c2_sharded": c2,

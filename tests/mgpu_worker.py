@@ -121,6 +121,20 @@ for mode in ("push", "pull"):
     del mb
 os.environ.pop("MDE_B200_ALLREDUCE", None)
 res["big"] = big
+
+# (v) a sharded problem the device solver does not take (arbitrary callable): the host-stepped solver must still see
+#     the GLOBAL objective (EdgeLayout all-reduces evaluations), so the replicas stay identical
+wq = torch.rand(len(edges), generator=torch.Generator().manual_seed(5)) + 0.5
+lo, hi = pdist.shard_range(len(edges), rank, world)
+wloc = wq[lo:hi].to(dev)
+mg = pm.MDE(n, m, et[lo:hi].to(dev), lambda d: wloc * d ** 2, pm.Centered(), device=dev)
+pdist.attach(mg, rank, world, len(edges), dev)
+Xg0 = torch.tensor(X0, device=dev)
+vg = mg.average_distortion(Xg0).item()
+vg_ref = float((wq.double().numpy() * (np.linalg.norm(X0[edges[:, 0]].astype(np.float64) - X0[edges[:, 1]], axis=1) ** 2)).mean())
+Xg = mg.embed(X=Xg0, max_iter=6, eps=0.0)
+res["generic"] = {"value_rel": abs(vg - vg_ref) / abs(vg_ref), "x_identical": digests_equal(Xg),
+                  "decreased": bool(mg.solve_stats.average_distortions[-1] < mg.solve_stats.average_distortions[0])}
 if rank == 0:
     print("MGPU_RESULT " + json.dumps(res), flush=True)
 td.barrier()

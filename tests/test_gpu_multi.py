@@ -46,6 +46,8 @@ def test_two_rank_sharded_evaluation_and_solve():
         assert t["iterations"] == 8 and t["x_identical"] and t["decreased"]
         assert t["loss0_rel"] < 1e-5 and t["resid0_rel"] < 1e-4
         assert t["first3_rel_vs_single"] < 1e-3
+    # (v) non-fused sharded problem (external callable -> host-stepped solver): global objective, identical replicas
+    assert r["generic"]["value_rel"] < 1e-5 and r["generic"]["x_identical"] and r["generic"]["decreased"]
     # (iii) converged problem: the north_star's criterion
     c = r["converged"]
     assert c["x_identical"] and c["iterations"] < 800 and c["single_iterations"] < 800
