@@ -117,7 +117,7 @@ struct PullArgs {
 // 4 CONSECUTIVE entries of one lane, class known.  Entries are sorted by owner: the lane keeps the sum of a run of
 // equal owners in registers (`cur`, `acc`, carried across the quads of one warp-tile) and issues one vector red when
 // the owner changes, so a long run costs one red per lane that holds a piece of it.
-template <int M, int MODE, int FA, int FR, bool FAST, int CLS>
+template <int M, int MODE, int FA, int FR, bool FAST, int CLS, bool PUSH>
 __device__ __forceinline__ void pull_quad(const PullArgs& a, const float* __restrict__ Xt, int ibase, int first_idx,
                                           int own_base, int cnt, const float (&w)[4], const int (&oo)[4],
                                           const int (&nl)[4], const float (&gx)[4], int& cur, float (&acc)[M],
@@ -150,7 +150,7 @@ __device__ __forceinline__ void pull_quad(const PullArgs& a, const float* __rest
     if (MODE != 2) {
       // every undirected edge is seen from both ends: count its distortion once, at the entry whose owner is
       // the smaller endpoint
-      const bool canon = ok && (own[e] < ibase + nl[e]);
+      const bool canon = ok && (PUSH || own[e] < ibase + nl[e]);  // a push entry is the edge's only entry
       if (canon) { if (FAST) lsum_f += f; else lsum += (double)f; }
     }
     if (MODE != 1) {
@@ -162,8 +162,15 @@ __device__ __forceinline__ void pull_quad(const PullArgs& a, const float* __rest
 #pragma unroll
         for (int c = 0; c < M; ++c) acc[c] = 0.0f;
       }
+      float v[M];
 #pragma unroll
-      for (int c = 0; c < M; ++c) acc[c] += live ? g * diff[c] : 0.0f;
+      for (int c = 0; c < M; ++c) { v[c] = live ? g * diff[c] : 0.0f; acc[c] += v[c]; }
+      if (PUSH && live) {  // the far endpoint of a push entry gets its contribution as one global red
+        float nv[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) nv[c] = -v[c];
+        p_red_row<M>(a.grad, ibase + nl[e], nv);
+      }
     }
   }
 }
@@ -302,11 +309,15 @@ distortion_pull_kernel(const PullArgs a) {
           gx[e] = __ldg(a.gext + (o > 0 ? (o >> 1) : 0));
         }
       }
+      // class of the warp-tile (header): 0 attractive / ordinary (mirrored: pull), 1 repulsive mirrored, 2 repulsive
+      // stored ONCE ("push": random pairs have no owner runs worth mirroring for)
       if (FAST) {
-        if (cls == 0) pull_quad<M, MODE, FA, FR, FAST, 0>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
-        else pull_quad<M, MODE, FA, FR, FAST, 1>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
+        if (cls == 0) pull_quad<M, MODE, FA, FR, FAST, 0, false>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
+        else if (cls == 1) pull_quad<M, MODE, FA, FR, FAST, 1, false>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
+        else pull_quad<M, MODE, FA, FR, FAST, 1, true>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
       } else {
-        pull_quad<M, MODE, FA, FR, FAST, 2>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
+        if (cls == 2) pull_quad<M, MODE, FA, FR, FAST, 2, true>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
+        else pull_quad<M, MODE, FA, FR, FAST, 2, false>(a, Xt, (int)base, first_idx, own_base, cnt, wq, oq, nq, gx, cur, acc, lsum_f, lsum);
       }
     }
     if (MODE != 1 && (EPL * lane) < cnt) p_red_row<M>(a.grad, cur, acc);
@@ -328,18 +339,24 @@ struct PKeyBits { int rb, ss, sb, shift_own, shift_bkt; int64_t ndt; };
 
 // entry k = (edge k >> 1, direction k & 1); key = (((owner super-tile * ndt + nbr tile) * 2 + class) | owner | nbr local)
 __global__ void pull_keys_kernel(const int64_t* __restrict__ edges, const float* __restrict__ par0, int push_pull,
-                                 int64_t p2, PKeyBits kb, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                 int hybrid, uint64_t drop_bkt, int64_t p2, PKeyBits kb, uint64_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= p2) return;
   const int64_t e = k >> 1;
   const int dir = (int)(k & 1);
-  const int64_t i = edges[2 * e], j = edges[2 * e + 1];
-  const uint64_t own = (uint64_t)(dir ? j : i), nbr = (uint64_t)(dir ? i : j);
+  int64_t i = edges[2 * e], j = edges[2 * e + 1];
   const uint64_t cls = (push_pull && !(par0[e] >= 0.0f)) ? 1ull : 0ull;
+  vals[k] = (uint32_t)k;
+  if (hybrid && cls) {
+    // repulsive edge stored once, owner = smaller endpoint; its mirror sorts behind every real bucket and is dropped
+    if (dir) { keys[k] = drop_bkt << kb.shift_bkt; return; }
+    if (i > j) { const int64_t t = i; i = j; j = t; }
+  }
+  const uint64_t own = (uint64_t)(dir ? j : i), nbr = (uint64_t)(dir ? i : j);
   const uint64_t bkt = (((own >> kb.ss) * (uint64_t)kb.ndt + (nbr >> kb.rb)) << 1) | cls;
   const uint64_t nl = nbr & ((1ull << kb.rb) - 1ull);
   keys[k] = (bkt << kb.shift_bkt) | (own << kb.rb) | nl;
-  vals[k] = (uint32_t)k;
 }
 
 __global__ void pull_starts_kernel(const uint64_t* __restrict__ keys, int64_t p2, int shift_bkt,
@@ -361,7 +378,7 @@ __global__ void pull_scatter_kernel(const uint64_t* __restrict__ keys, const uin
                                     const float* __restrict__ par0, int64_t p2, PKeyBits kb,
                                     const int32_t* __restrict__ slot_shift, const int32_t* __restrict__ grp_end,
                                     int32_t* __restrict__ rec, int32_t* __restrict__ perm, int* __restrict__ bad,
-                                    int epl) {
+                                    int epl, int hybrid, const int32_t* __restrict__ wt_perm) {
   const int NE = 32 * epl, kRecWords = rec_words(epl);
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= p2) return;
@@ -372,7 +389,7 @@ __global__ void pull_scatter_kernel(const uint64_t* __restrict__ keys, const uin
   const int32_t nl = (int32_t)(key & ((1ull << kb.rb) - 1ull));
   const uint32_t v = vals[k];
   const int64_t slot = k + (int64_t)slot_shift[b];
-  const int64_t t = slot / NE;
+  const int64_t t = (int64_t)wt_perm[slot / NE];  // physical position of this (logical) warp-tile
   const int j = (int)(slot % NE);
   const int64_t k0 = k - j;  // first entry of this warp-tile (same group: groups start on warp-tile boundaries)
   const int32_t own0 = (int32_t)((keys[k0] >> kb.rb) & own_mask);
@@ -382,13 +399,13 @@ __global__ void pull_scatter_kernel(const uint64_t* __restrict__ keys, const uin
   r[j] = __float_as_int(par0[v >> 1]);
   reinterpret_cast<unsigned short*>(r + NE)[j] = (unsigned short)off;
   reinterpret_cast<unsigned short*>(r + NE + NE / 2)[j] = (unsigned short)nl;
-  perm[slot] = (int32_t)v;
+  perm[t * NE + j] = (int32_t)v;
   if (j == 0) {
     const int64_t left = (int64_t)grp_end[b] - k0;
     const int cnt = (int)(left < NE ? left : NE);
     r[2 * NE] = own0;
     r[2 * NE + 1] = cnt;
-    r[2 * NE + 2] = (int32_t)(b & 1ull);
+    r[2 * NE + 2] = (b & 1ull) ? (hybrid ? 2 : 1) : 0;
     r[2 * NE + 3] = 0;
     // pads of a partial warp-tile repeat the last valid owner / neighbour so that they extend the last run
     if (cnt < NE) {
@@ -508,7 +525,10 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
   const int64_t p2 = 2 * p;
   int rb = (m <= 2) ? 13 : 12;  // X tile of 64 KB (m = 1: 32 KB)
   { const int r = penv_int("MDE_B200_TILE_RB", 0); if (r >= 8 && r <= 15) rb = r; }
-  const int epl = penv_int("MDE_B200_PULL_EPL", 8) == 4 ? 4 : 8;  // entries per lane per warp-tile
+  // entries per lane per warp-tile: 8 amortises the per-record work (C3-shaped: 125 vs 135 us) but needs enough
+  // records to keep 32 warps x 148 SMs busy; smaller problems take 4 (C2: 18.4 vs 22.5 us)
+  int epl = (p2 / 256 >= 8ll * kPullWarps * kNumSMs) ? 8 : 4;
+  { const int ev = penv_int("MDE_B200_PULL_EPL", 0); if (ev == 4 || ev == 8) epl = ev; }
   const int NE = 32 * epl, kRecWords = rec_words(epl), kRecBytes = rec_bytes(epl);
   if (rb > 16 || pull_smem_bytes(rb, m, epl) > 227u * 1024u) return MDE_E_UNSUPPORTED;
   int64_t l2_bytes = (int64_t)penv_int("MDE_B200_STILE_MB", 48) << 20;
@@ -518,10 +538,17 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
   const int64_t ndt = (n + R - 1) >> rb, nst = (n + S - 1) >> ss;
   const int64_t nb_all = ndt * nst * 2;
   if (nb_all > (1ll << 22)) return MDE_E_UNSUPPORTED;
+  // Hybrid (MDE_B200_PULL_REP=push; off by default): repulsive edges of PushAndPull are uniformly random pairs -- an
+  // owner has ~1 of them per neighbour tile, so mirroring them doubles the work without creating runs.  Stored ONCE
+  // ("push" entries: neighbour row from the shared tile, far-endpoint contribution as one global red) they cut the
+  // instructions by 20 % (7.8 M -> 6.2 M at C2) but add 0.9 M L2 requests for the reds: 22.5 us against 20.5 us
+  // mirrored (profiles/r02_kernels.md), so mirroring stays the default.
+  int hybrid = 0;
+  { const char* ev = getenv("MDE_B200_PULL_REP"); if (ev && !strcmp(ev, "push") && fn->push_pull) hybrid = 1; }
   PKeyBits kb;
   kb.rb = rb; kb.ss = ss; kb.sb = pbits_for((uint64_t)(n - 1)); kb.ndt = ndt;
   kb.shift_own = rb; kb.shift_bkt = kb.sb + rb;
-  const int total_bits = kb.shift_bkt + pbits_for((uint64_t)(nb_all - 1));
+  const int total_bits = kb.shift_bkt + pbits_for((uint64_t)nb_all);  // bucket id nb_all = dropped mirrors
   if (total_bits > 64) return MDE_E_UNSUPPORTED;
 
   uint64_t *keys_in = nullptr, *keys_out = nullptr;
@@ -531,7 +558,8 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
   int rc = 0;
-  std::vector<int32_t> start, shift, gend, bkt_tile, bkt_wt0, cta_wt0, cta_bkt0, wt_tile;
+  std::vector<int32_t> start, shift, gend, bkt_tile, bkt_wt0, cta_wt0, cta_bkt0, wt_tile, wt_perm;
+  int32_t* perm_d = nullptr;
 #define TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = (int)_e; goto done; } } while (0)
   {
     const int tb = 256;
@@ -540,27 +568,32 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
     TRY(cudaMalloc(&keys_out, sizeof(uint64_t) * p2));
     TRY(cudaMalloc(&vals_in, sizeof(uint32_t) * p2));
     TRY(cudaMalloc(&vals_out, sizeof(uint32_t) * p2));
-    TRY(cudaMalloc(&start_d, sizeof(int32_t) * nb_all));
+    TRY(cudaMalloc(&start_d, sizeof(int32_t) * (nb_all + 1)));
     TRY(cudaMalloc(&shift_d, sizeof(int32_t) * nb_all));
     TRY(cudaMalloc(&end_d, sizeof(int32_t) * nb_all));
     TRY(cudaMalloc(&bad_d, sizeof(int)));
     TRY(cudaMemsetAsync(bad_d, 0, sizeof(int), st));
-    pull_keys_kernel<<<nbk, tb, 0, st>>>(edges, par0, fn->push_pull, p2, kb, keys_in, vals_in);
+    pull_keys_kernel<<<nbk, tb, 0, st>>>(edges, par0, fn->push_pull, hybrid, (uint64_t)nb_all, p2, kb, keys_in, vals_in);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());
     TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p2, 0, total_bits, st));
     TRY(cudaMalloc(&tmp, tmp_bytes));
     TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)p2, 0, total_bits, st));
-    TRY(cudaMemsetAsync(start_d, 0xFF, sizeof(int32_t) * nb_all, st));
+    TRY(cudaMemsetAsync(start_d, 0xFF, sizeof(int32_t) * (nb_all + 1), st));
     pull_starts_kernel<<<nbk, tb, 0, st>>>(keys_out, p2, kb.shift_bkt, start_d);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());
-    start.resize(nb_all);
-    TRY(cudaMemcpyAsync(start.data(), start_d, sizeof(int32_t) * nb_all, cudaMemcpyDeviceToHost, st));
+    start.resize(nb_all + 1);
+    TRY(cudaMemcpyAsync(start.data(), start_d, sizeof(int32_t) * (nb_all + 1), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
+    const int64_t p2_eff = (start[nb_all] >= 0) ? (int64_t)start[nb_all] : p2;  // entries before the dropped mirrors
 
     shift.assign(nb_all, 0);
     gend.assign(nb_all, 0);
+    // logical order: buckets (owner super-tile, neighbour tile, class) one after the other, each padded to whole
+    // warp-tiles.  lb_* describe the non-empty buckets in that order.
+    std::vector<int64_t> lb_id;
+    std::vector<int32_t> lb_wt0;
     int64_t slot = 0, prev_b = -1;
     for (int64_t b = 0; b < nb_all; ++b) {
       if (start[b] < 0) continue;
@@ -569,20 +602,45 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
         const int64_t cnt = (int64_t)start[b] - (int64_t)start[prev_b];
         slot += (cnt + NE - 1) / NE * NE;
       }
-      bkt_tile.push_back((int32_t)((b >> 1) % ndt));
-      bkt_wt0.push_back((int32_t)(slot / NE));
+      lb_id.push_back(b);
+      lb_wt0.push_back((int32_t)(slot / NE));
       shift[b] = (int32_t)(slot - (int64_t)start[b]);
       prev_b = b;
     }
     if (prev_b < 0) { rc = MDE_E_INVALID; goto done; }
-    gend[prev_b] = (int32_t)p2;
-    slot += (p2 - (int64_t)start[prev_b] + NE - 1) / NE * NE;
+    gend[prev_b] = (int32_t)p2_eff;
+    slot += (p2_eff - (int64_t)start[prev_b] + NE - 1) / NE * NE;
     if (slot >= (1ll << 31)) { rc = MDE_E_UNSUPPORTED; goto done; }
     const int64_t nwt = slot / NE;
+    lb_wt0.push_back((int32_t)nwt);
+    const int nlb = (int)lb_id.size();
+    const int64_t min_per_bucket = penv_int("MDE_B200_TILE_MIN", 2048);
+    if (nlb > 2 && p2_eff / nlb < min_per_bucket) { rc = MDE_E_UNSUPPORTED; goto done; }
+    // physical order: the two classes of one (super-tile, tile) group share the resident X tile, so their warp-tiles
+    // are INTERLEAVED proportionally -- pull (issue-bound) and push (red-bound) records then alternate inside every
+    // CTA instead of filling different CTAs (measured: contiguous classes left the push CTAs 3.5x longer than the rest).
+    // The kernel sees one bucket per group; wt_perm maps a logical warp-tile to its physical position.
+    wt_perm.assign(nwt, 0);
+    for (int i0 = 0; i0 < nlb;) {
+      int i1 = i0 + 1;
+      if (i1 < nlb && (lb_id[i1] >> 1) == (lb_id[i0] >> 1)) ++i1;  // the group's second class
+      const int32_t g0 = lb_wt0[i0], g1 = lb_wt0[i1];
+      bkt_tile.push_back((int32_t)((lb_id[i0] >> 1) % ndt));
+      bkt_wt0.push_back(g0);
+      if (i1 - i0 == 2) {
+        const int32_t nA = lb_wt0[i0 + 1] - g0, nB = g1 - lb_wt0[i0 + 1];
+        int32_t ia = 0, ib = 0;
+        for (int32_t t = g0; t < g1; ++t) {  // next record from the class that is behind its share
+          const bool takeA = (ib >= nB) || (ia < nA && (int64_t)ia * nB <= (int64_t)ib * nA);
+          if (takeA) wt_perm[g0 + ia++] = t; else wt_perm[lb_wt0[i0 + 1] + ib++] = t;
+        }
+      } else {
+        for (int32_t t = g0; t < g1; ++t) wt_perm[t] = t;
+      }
+      i0 = i1;
+    }
     bkt_wt0.push_back((int32_t)nwt);
     const int nbkt = (int)bkt_tile.size();
-    const int64_t min_per_bucket = penv_int("MDE_B200_TILE_MIN", 2048);
-    if (nbkt > 2 && p2 / nbkt < min_per_bucket) { rc = MDE_E_UNSUPPORTED; goto done; }
 
     const int ncta = (int)std::min<int64_t>(kNumSMs, std::max<int64_t>(1, (nwt + 1) / 2));
     cta_wt0.resize(ncta + 1);
@@ -610,10 +668,13 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
     TRY(cudaMemcpyAsync(e->cta_wt0, cta_wt0.data(), sizeof(int32_t) * (ncta + 1), cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(e->cta_bkt0, cta_bkt0.data(), sizeof(int32_t) * ncta, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(e->wt_tile, wt_tile.data(), sizeof(int32_t) * nwt, cudaMemcpyHostToDevice, st));
+    TRY(cudaMalloc(&perm_d, sizeof(int32_t) * nwt));
+    TRY(cudaMemcpyAsync(perm_d, wt_perm.data(), sizeof(int32_t) * nwt, cudaMemcpyHostToDevice, st));
     pull_fill_kernel<<<ceil_div_i64(nwt * kRecWords, tb), tb, 0, st>>>(e->rec, e->perm, nwt, epl);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());
-    pull_scatter_kernel<<<nbk, tb, 0, st>>>(keys_out, vals_out, par0, p2, kb, shift_d, end_d, e->rec, e->perm, bad_d, epl);
+    pull_scatter_kernel<<<ceil_div_i64(p2_eff, tb), tb, 0, st>>>(keys_out, vals_out, par0, p2_eff, kb, shift_d, end_d, e->rec,
+                                                               e->perm, bad_d, epl, hybrid, perm_d);
     ++g_launch_count;
     TRY(cudaPeekAtLastError());
     int bad = 0;
@@ -632,7 +693,7 @@ int pull_build(mde_edges* e, const int64_t* edges, const float* par0, const mde_
   }
 done:
   cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(vals_out); cudaFree(start_d); cudaFree(shift_d);
-  cudaFree(end_d); cudaFree(bad_d); cudaFree(tmp);
+  cudaFree(end_d); cudaFree(bad_d); cudaFree(tmp); cudaFree(perm_d);
   if (rc != 0) {
     tiled_free(e);
     pull_free(e);
