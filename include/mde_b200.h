@@ -187,6 +187,12 @@ int mde_solver_begin_ex(mde_solver_t* s, const float* X0, double eps, int max_it
  * *converged = 1 if the residual test fired.  Returns MDE_E_NAN where the reference raises
  * SolverError. */
 int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, void* stream);
+
+/* Diagnostics: %globaltimer stamps (ns) of the last step that started an iteration (mode 2, late-epilogue chain):
+ * [0] entry of the head kernel's last block, [1] its scalar stage begins, [2] solver state staged in shared memory,
+ * [3] partials reduced, [4] previous step finished / phase chosen, [5] history update + two-loop done,
+ * [6] before the state is written back, [7] first block of the vector kernel that follows.  No reference counterpart. */
+int mde_solver_debug_times(mde_solver_t* s, unsigned long long* out8, void* stream);
 /* Device pointer to the current iterate (n,m). */
 float* mde_solver_x(mde_solver_t* s);
 /* Copy statistics to host arrays of length >= iterations done (blocking):

@@ -47,8 +47,16 @@ constexpr int kVecBlocks = kNumSMs * 2;
 constexpr int kPairsPerSlice = 10;  // the default history (memory_size = 10, optim.py:110) fits ONE slice: one wave
 constexpr int kDotsPerSlice = 4 + 5 * kPairsPerSlice;  // 54
 constexpr int kMaxSlices = (kMaxMemory + kPairsPerSlice - 1) / kPairsPerSlice;  // 4
+constexpr int kHeadAcc = kDotsPerSlice + 12;  // step_head_kernel: + g.d, g.g, |g|_1, column sums of g and X (+ pad): fp32 accumulators
+constexpr int kHeadCols = kHeadAcc + 6;       // columns of a partial row: + loss, (g.d, d.d, X.X, max|d|) of the vec kernel, pad (even)
 constexpr int kStatusInts = 12;
 enum { PH_DIR = 0, PH_TRIAL = 1, PH_FRESH = 2, PH_MAT = 3 };  // mode 2: phase of a step
+
+struct alignas(16) HeadDesc {  // what every block of the next head kernel needs, in 64 bytes (4 broadcast loads)
+  int pend, phase, count, n_iter;
+  int cand; float t_cur, t_last; int pad;
+  unsigned char order[32];   // logical -> physical slot of the stored pairs (kMaxMemory <= 32)
+};
 
 struct SolverState {
   // ---- status word (first kStatusInts ints, copied to the host) ----
@@ -64,7 +72,7 @@ struct SolverState {
   int paused;      // stopped at iter_limit; mde_solver_run resumes it
   int phase;       // what the next step does (PH_*)
   int iter_limit;  // pause when `iter` reaches it
-  int pad1;
+  int pend;        // late-epilogue steps: 1 = the previous step executed phase `phase`, its bookkeeping is pending
   int g_dir;       // gates of the next step, written by the step epilogue: direction kernels run
   int g_eval;      //   closure evaluation (scatter kernel, tangent projection, dots) runs
   int g_mat;       //   the axpy materialises the ACCEPTED point (no evaluation follows)
@@ -84,6 +92,12 @@ struct SolverState {
   int max_stats;
   int world;
   double *avg, *resid, *pct, *steplen;
+  // ---- late-epilogue steps ----
+  double t_cur;                      // step length the current step's vec kernel applies (t0 / ls.t / ls.t_accept)
+  double cs_g[4], cs_d[4];           // column sums of g_prev and d (tracked through the two-loop coefficients)
+  double cs_S[kSlots][4], cs_Y[kSlots][4];  // ... and of the stored pairs
+  HeadDesc hd;                       // written by init / the head kernel's epilogue for the NEXT head kernel
+  unsigned long long dbg[12];        // globaltimer stamps of the last head kernel that started an iteration (mde_solver_debug_times)
   LsState ls;
   LbfgsState lb;
 };
@@ -156,6 +170,7 @@ struct Tail {              // what a fused scalar epilogue needs
   const float* tail;       // (hi, lo) of the all-reduced loss (multi-GPU)
   double p_total;
   int64_t n_rows;
+  double inv_n;            // 1 / n_rows
   cudaGraphConditionalHandle h_while;
 };
 
@@ -1176,6 +1191,496 @@ __device__ void step_end_body(SolverState* __restrict__ S, const double* __restr
   set_phase(S, next);
 }
 
+// ---------------------------------------------------------------------------------------
+// mode 2, "late epilogue" steps (default; MDE_B200_LATE=0 keeps the chain above).  A step is
+//     head -> vec -> [retraction kernels] -> scatter [-> all-reduce] [-> tangent projection]
+// with ONE scalar stage, in the head kernel's last block:
+//   head  reads g, g_prev, d, X and the history once: (g.d, g.g, |g|_1) of the evaluation the previous step left
+//         pending, the history dots of the iteration that would start if that trial is accepted, column sums of g and
+//         X (Centered).  Its blocks also fold the previous scatter launch's loss partials and the previous vec
+//         kernel's (g.d, d.d, X.X, max|d|) partials into their rows, so the epilogue does one reduction.  Epilogue:
+//         finish the previous step (line-search init if it was PH_DIR, Wolfe update, end of iteration), choose this
+//         step's phase, and when an iteration starts: history update, two-loop, first step length, column means.
+//   vec   PH_DIR: d = H g, g_prev = g, x_init = X and the first trial X = x_init + t0 d in ONE pass (t0 does not
+//         depend on g.d: lbfgs.py:521-530); PH_TRIAL / PH_MAT: X = x_init + t d; every phase but PH_MAT: g = 0.
+// 3 kernels and one one-block epilogue per evaluation instead of 5 and 3.  The history dots are SPECULATIVE (they
+// assume the trial just evaluated, t = t_cur, is accepted, which the strong-Wolfe search does ~9 times out of 10);
+// when it asks for another trial they are unused, when it accepts an earlier point (PH_MAT) the step after the
+// materialisation recomputes them with the accepted t.
+// ---------------------------------------------------------------------------------------
+constexpr int kColG = kDotsPerSlice + 3;   // 57: column sums of g (4)
+constexpr int kColX = kDotsPerSlice + 7;   // 61: column sums of X (4)
+constexpr int kColLoss = kHeadAcc;         // 66: loss partial sum of the pending evaluation
+constexpr int kColVec = kHeadAcc + 1;      // 67..70: g.d, d.d, X.X, max|d| of the pending PH_DIR step (max last)
+
+__device__ void fill_head_desc(SolverState* S) {
+  HeadDesc& h = S->hd;
+  h.pend = S->pend; h.phase = S->phase; h.count = S->lb.count; h.n_iter = S->lb.n_iter; h.cand = S->lb.cand;
+  h.t_cur = (float)S->t_cur; h.t_last = (float)S->t_last; h.pad = 0;
+  for (int j = 0; j < 32; ++j) h.order[j] = (unsigned char)((j < kSlots) ? S->lb.order[j] : 0);
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ void fresh_apply(SolverState* __restrict__ S, double loss, double gg, double g1) {
+  S->loss = loss; S->gg = gg; S->g1 = g1;
+  S->func_evals += 1;
+  S->pad0 = (int)S->func_evals;
+}
+
+__device__ void ls_apply(SolverState* __restrict__ S, double loss, double gtd, double gg, double g1) {
+  S->gg = gg; S->g1 = g1;
+  S->func_evals += 1;
+  S->pad0 = (int)S->func_evals;
+  LsState L = S->ls;
+  S->t_eval = L.t;
+  ls_on_result(L, loss, (float)gtd, isfinite(gg));
+  S->ls = L;
+  if (L.phase == LS_DONE) {
+    S->ls_active = 0;
+    if (L.error) { S->error = MDE_E_NAN; S->active = 0; }
+    S->t_last = L.t_accept;
+    S->loss = (double)(float)L.f_accept;  // _cached_loss is an fp32 tensor (lbfgs.py:550)
+  }
+}
+
+// The scalar stage of a late-epilogue step (last block of the head kernel).  The whole SolverState (history Gram
+// matrices included, ~21 KB) is staged into shared memory with one cooperative copy, the phase machine, the
+// line search and the two-loop recursion run on that copy, and it is written back once at the end: the serial
+// part never waits for an L2 round trip.
+constexpr int kStateDoubles = (int)(sizeof(SolverState) / sizeof(double));
+constexpr int kLbOffsetDoubles = (int)(offsetof(SolverState, lb) / sizeof(double));
+constexpr int kHeadSmemBytes = (int)(sizeof(SolverState) + sizeof(double) * (kMaxSlices * kHeadCols + 5 * kSlots) + 64);
+static_assert(sizeof(SolverState) % sizeof(double) == 0 && offsetof(SolverState, lb) % sizeof(double) == 0, "staged as doubles");
+
+// Fixed-order reduction of the head kernel's partial rows (kHeadCols doubles each, 16-byte aligned) into out[]:
+// thread (segment, column pair) loads its rows as double2 -- all loads of a thread in flight together, one L2 round
+// trip for <= 296 rows -- and adds them with two independent accumulators; then thread k combines the segments
+// serially.  Dependent fp64 chains are what the one-block stage waits for (DADD + SHFL trees cost ~100 cycles a
+// level with 8 resident warps), so there is no shuffle tree here.  Column `kmax` is a maximum, the others sums.
+__device__ void reduce_head_rows(const double* __restrict__ part, int nb, double* __restrict__ out, int kmax) {
+  constexpr int KP = kHeadCols / 2;            // column pairs
+  constexpr int SEG = 256 / KP;                // segments
+  constexpr int RB = 22;                       // rows per thread in flight (one batch covers 154 rows)
+  __shared__ double red[SEG][kHeadCols];
+  const int cp = threadIdx.x % KP, seg = threadIdx.x / KP;
+  if (seg < SEG) {
+    const bool mx = (2 * cp == kmax);
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    for (int base = seg; base < nb; base += RB * SEG) {
+      double2 v[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int b = base + r * SEG;
+        v[r] = (b < nb) ? __ldcg(reinterpret_cast<const double2*>(part + (int64_t)b * kHeadCols) + cp) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int r = 0; r < RB; r += 2) {
+        a0 = mx ? fmax(a0, v[r].x) : a0 + v[r].x; a1 = mx ? fmax(a1, v[r + 1].x) : a1 + v[r + 1].x;
+        b0 += v[r].y; b1 += v[r + 1].y;
+      }
+    }
+    red[seg][2 * cp] = mx ? fmax(a0, a1) : a0 + a1;
+    red[seg][2 * cp + 1] = b0 + b1;
+  }
+  __syncthreads();
+  if (threadIdx.x < kHeadCols) {
+    const bool mx = ((int)threadIdx.x == kmax);
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int q = 0; q + 1 < SEG; q += 2) {
+      a0 = mx ? fmax(a0, red[q][threadIdx.x]) : a0 + red[q][threadIdx.x];
+      a1 = mx ? fmax(a1, red[q + 1][threadIdx.x]) : a1 + red[q + 1][threadIdx.x];
+    }
+    if (SEG & 1) a0 = mx ? fmax(a0, red[SEG - 1][threadIdx.x]) : a0 + red[SEG - 1][threadIdx.x];
+    out[threadIdx.x] = mx ? fmax(a0, a1) : a0 + a1;
+  }
+  __syncthreads();
+}
+
+__device__ void step_head_body(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks, Tail tl,
+                               unsigned char* smem, float tpass, unsigned long long t_entry) {
+  SolverState* sS = reinterpret_cast<SolverState*>(smem);
+  double* sums = reinterpret_cast<double*>(smem + sizeof(SolverState));
+  double* dots = sums + kMaxSlices * kHeadCols;
+  int* flags = reinterpret_cast<int*>(dots + 5 * kSlots);
+  __shared__ int s_go, s_dirty;
+  __shared__ unsigned long long s_t[8];
+  if (threadIdx.x == 0) s_t[0] = gtime();
+  {
+    const double* src = reinterpret_cast<const double*>(S);
+    double* dst = reinterpret_cast<double*>(sS);
+    for (int k = threadIdx.x; k < kStateDoubles; k += blockDim.x) dst[k] = __ldcg(src + k);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_t[1] = gtime();
+  const int pend = sS->pend, prev = sS->phase, count = sS->lb.count, n_iter = sS->lb.n_iter;
+  int slices = (count + kPairsPerSlice - 1) / kPairsPerSlice;
+  if (slices < 1) slices = 1;
+  for (int sl = 0; sl < slices; ++sl)
+    reduce_head_rows(part + (int64_t)sl * nblocks * kHeadCols, nblocks, sums + sl * kHeadCols, kColVec + 3);
+  if (threadIdx.x == 0) {
+    s_t[2] = gtime();
+    if (pend) {  // ---- finish the previous step ----
+      double lsum = sums[kColLoss];
+      if (sS->world > 1) lsum = (double)tl.tail[0] + (double)tl.tail[1];
+      const double loss = (double)(float)(lsum / tl.p_total);  // fp32 mean as the reference sees it
+      const double gtd = sums[kDotsPerSlice], gg = sums[kDotsPerSlice + 1], g1 = sums[kDotsPerSlice + 2];
+      if (prev == PH_FRESH) fresh_apply(sS, loss, gg, g1);
+      else if (prev != PH_MAT) {
+        if (prev == PH_DIR) {  // the line-search init the vec kernel could not do (lbfgs.py:521-549)
+          sS->gtd = (float)sums[kColVec]; sS->dd = sums[kColVec + 1]; sS->xx = sums[kColVec + 2];
+          sS->dmax = (float)sums[kColVec + 3];
+          ls_begin(sS->ls, sS->t_cur, sS->loss, (float)sums[kColVec], (float)sums[kColVec + 3]);
+          sS->ls_active = 1;
+        }
+        ls_apply(sS, loss, gtd, gg, g1);
+      }
+      if (sS->error == MDE_E_COMM) sS->active = 0;
+      int next = prev;
+      bool end_of_iteration = false;
+      if (prev == PH_FRESH) next = PH_DIR;
+      else if (prev == PH_MAT) end_of_iteration = true;
+      else if (sS->ls_active) next = PH_TRIAL;
+      else if (sS->active) {
+        if (sS->ls.t_accept == sS->t_eval) end_of_iteration = true;
+        else next = PH_MAT;
+      }
+      if (end_of_iteration) {
+        iter_end_body(sS, 0);
+        next = sS->need_fresh ? PH_FRESH : PH_DIR;
+        if (sS->active && sS->iter >= sS->iter_limit) { sS->active = 0; sS->paused = 1; }
+      }
+      set_phase(sS, next);
+      if (next == PH_TRIAL) sS->t_cur = sS->ls.t;
+      else if (next == PH_MAT) sS->t_cur = sS->ls.t_accept;
+      sS->pend = 0;
+    }
+    s_go = (sS->active && sS->phase == PH_DIR) ? 1 : 0;
+    s_dirty = (s_go || sS->lb.n_iter != n_iter) ? 1 : 0;  // (opt.reset() at the end of an iteration)
+    s_t[3] = gtime();
+  }
+  __syncthreads();
+  // ---- this step starts an iteration: history update + two-loop (the sums are those of THIS pass: valid because
+  //      the accepted step is the one the pass assumed, or it ran with t_last after a pause / PH_MAT) ----
+  if (s_go) {
+    LbfgsState& B = sS->lb;
+    if (threadIdx.x == 0) {
+      // callback of LBFGS.step (optim.py:94-96): loss and ||X.grad||_F at the iteration start
+      const int it = sS->iter;
+      const double resid = (double)sqrtf((float)sS->gg);
+      if (it < sS->max_stats) { sS->avg[it] = sS->loss; sS->resid[it] = resid; }
+      sS->stop_after = (resid <= sS->eps) ? 1 : 0;
+    }
+    if ((int)threadIdx.x < count) {
+      const int j = threadIdx.x;
+      const double* b = sums + (j / kPairsPerSlice) * kHeadCols + 4 + 5 * (j % kPairsPerSlice);
+      dots[j] = b[0]; dots[kSlots + j] = b[1]; dots[2 * kSlots + j] = b[2]; dots[3 * kSlots + j] = b[3];
+      dots[4 * kSlots + j] = b[4];
+    }
+    __syncthreads();
+    if (n_iter > 0) lbfgs_direction_block(B, dots, sums[0], sums[1], sums[2], sums[3], flags);
+    else lbfgs_direction_block(B, dots, 0.0, 0.0, 0.0, 0.0, flags);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_t[4] = gtime();
+      double t0 = 1.0;
+      if (B.n_iter == 1) {  // t = min(1, 1/||g||_1) * lr
+        const float inv = 1.0f / (float)sS->g1;
+        t0 = (inv < 1.0f) ? (double)inv : 1.0;
+      }
+      sS->t_cur = t0;
+    }
+    if (threadIdx.x < 32) {
+      // column sums of d = cg g + sum_j cs_j S_j + cy_j Y_j from TRACKED column sums of the stored pairs
+      // (S_c = t d_prev, Y_c = g - g_prev), lane j owning pair j.  These are rounding-level quantities (the gradient
+      // of a translation-invariant objective sums to zero) and x's measured column mean corrects them every
+      // iteration: fp32 shuffles, not an fp64 tree.
+      const int lane = threadIdx.x;
+      if (!flags[0] && flags[1] && lane < 4) {
+        const int slot = B.order[B.count - 1];
+        sS->cs_S[slot][lane] = (double)tpass * sS->cs_d[lane];
+        sS->cs_Y[slot][lane] = sums[kColG + lane] - sS->cs_g[lane];
+      }
+      __syncwarp();
+      const int q = (lane < B.count) ? B.order[lane] : 0;
+      const float a = (lane < B.count) ? (float)B.cs[lane] : 0.0f, b = (lane < B.count) ? (float)B.cy[lane] : 0.0f;
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = a * (float)sS->cs_S[q][c] + b * (float)sS->cs_Y[q][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] += __shfl_xor_sync(kFull, v[c], o);
+      }
+      __syncwarp();
+      if (lane < 4) {
+        const float vl = lane == 0 ? v[0] : (lane == 1 ? v[1] : (lane == 2 ? v[2] : v[3]));
+        const double cd = B.cg * sums[kColG + lane] + (double)vl;
+        sS->cs_d[lane] = cd; sS->cs_g[lane] = sums[kColG + lane];
+        sS->mu_d[lane] = (float)(cd * tl.inv_n);
+        sS->mu_x[lane] = (float)(sums[kColX + lane] * tl.inv_n);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    sS->pend = sS->active ? 1 : 0;
+    fill_head_desc(sS);
+    if (s_go) {
+      s_t[5] = gtime();
+      sS->dbg[0] = t_entry;
+      for (int k = 0; k < 6; ++k) sS->dbg[1 + k] = s_t[k];
+    }
+  }
+  __syncthreads();
+  {
+    double* dst = reinterpret_cast<double*>(S);
+    const double* src = reinterpret_cast<const double*>(sS);
+    const int n = s_dirty ? kStateDoubles : kLbOffsetDoubles;  // the history state only when it changed
+    for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+  }
+}
+
+__global__ void __launch_bounds__(kVecThreads, 2)
+step_head_kernel(SolverState* __restrict__ S, const float* __restrict__ g, const float* __restrict__ gprev,
+                 const float* __restrict__ d, const float* __restrict__ X, float* __restrict__ Sb,
+                 float* __restrict__ Yb, int64_t npad, int mcols, double* __restrict__ part,
+                 const double* __restrict__ vpart, Tail tl) {
+  if (off(&S->active)) return;
+  constexpr int kHalf = kHeadAcc / 2;
+  __shared__ __align__(16) unsigned char raw[sizeof(float) * kHalf * kVecThreads];
+  static_assert(sizeof(raw) >= kHeadSmemBytes, "scalar epilogue must fit in the reduction tile");
+  __shared__ const float* sp[kPairsPerSlice];
+  __shared__ const float* yp[kPairsPerSlice];
+  const unsigned long long t_entry = gtime();
+  const int slice = blockIdx.y;
+  // one round trip: the 64-byte descriptor the previous epilogue left (same address for every thread)
+  const int4 h0 = __ldcg(reinterpret_cast<const int4*>(&S->hd));
+  const int4 h1 = __ldcg(reinterpret_cast<const int4*>(&S->hd) + 1);
+  const uint4 h2 = __ldcg(reinterpret_cast<const uint4*>(&S->hd) + 2);
+  const uint4 h3 = __ldcg(reinterpret_cast<const uint4*>(&S->hd) + 3);
+  const int pend = h0.x, prev = h0.y, count = h0.z, n_iter0 = h0.w;
+  const bool want_grad = pend && prev != PH_MAT && slice == 0;
+  const bool want_hist = (n_iter0 != 0) && !(pend && prev == PH_FRESH) && (slice == 0 || slice * kPairsPerSlice < count);
+  const bool spec = pend && (prev == PH_DIR || prev == PH_TRIAL);
+  const float t = spec ? __int_as_float(h1.y) : __int_as_float(h1.z);
+  float acc[kHeadAcc];
+#pragma unroll
+  for (int k = 0; k < kHeadAcc; ++k) acc[k] = 0.0f;
+  if (want_grad || want_hist || slice == 0) {
+    float* sc = Sb + (int64_t)h1.x * npad;
+    float* yc = Yb + (int64_t)h1.x * npad;
+    if (threadIdx.x < kPairsPerSlice) {
+      const int lj = slice * kPairsPerSlice + threadIdx.x;
+      const unsigned ow[8] = {h2.x, h2.y, h2.z, h2.w, h3.x, h3.y, h3.z, h3.w};
+      unsigned word = ow[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) if ((lj >> 2) == q) word = ow[q];
+      const int q = (lj < count && lj < 32) ? (int)((word >> (8 * (lj & 3))) & 0xffu) : 0;
+      sp[threadIdx.x] = Sb + (int64_t)q * npad;
+      yp[threadIdx.x] = Yb + (int64_t)q * npad;
+    }
+    __syncthreads();
+    int nval = want_hist ? count - slice * kPairsPerSlice : 0;
+    if (nval > kPairsPerSlice) nval = kPairsPerSlice;
+    const int64_t n4 = npad >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 G = reinterpret_cast<const float4*>(g)[i];
+      const float gv[4] = {G.x, G.y, G.z, G.w};
+      if (slice == 0) {
+        const float4 Xv = reinterpret_cast<const float4*>(X)[i];
+        // column sums (rows are m floats; 4 % m == 0 so element q of a float4 belongs to column q % m)
+        if (mcols == 1) {
+          acc[kColG] += (G.x + G.y) + (G.z + G.w); acc[kColX] += (Xv.x + Xv.y) + (Xv.z + Xv.w);
+        } else if (mcols == 2) {
+          acc[kColG] += G.x + G.z; acc[kColG + 1] += G.y + G.w; acc[kColX] += Xv.x + Xv.z; acc[kColX + 1] += Xv.y + Xv.w;
+        } else if (mcols == 4) {
+          acc[kColG] += G.x; acc[kColG + 1] += G.y; acc[kColG + 2] += G.z; acc[kColG + 3] += G.w;
+          acc[kColX] += Xv.x; acc[kColX + 1] += Xv.y; acc[kColX + 2] += Xv.z; acc[kColX + 3] += Xv.w;
+        }
+      }
+      if (!(want_grad || want_hist)) continue;
+      const float4 P = reinterpret_cast<const float4*>(gprev)[i];
+      const float4 D = reinterpret_cast<const float4*>(d)[i];
+      const float dv[4] = {D.x, D.y, D.z, D.w};
+      const float yv[4] = {G.x - P.x, G.y - P.y, G.z - P.z, G.w - P.w};
+      const float sv[4] = {D.x * t, D.y * t, D.z * t, D.w * t};
+      if (want_grad) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[kDotsPerSlice] += gv[q] * dv[q];
+          acc[kDotsPerSlice + 1] += gv[q] * gv[q];
+          acc[kDotsPerSlice + 2] += fabsf(gv[q]);
+        }
+      }
+      if (want_hist && slice == 0) {
+        reinterpret_cast<float4*>(yc)[i] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+        reinterpret_cast<float4*>(sc)[i] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[0] += yv[q] * sv[q]; acc[1] += yv[q] * yv[q];
+          acc[2] += sv[q] * gv[q]; acc[3] += yv[q] * gv[q];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kPairsPerSlice; ++j) {
+        if (j < nval) {
+          const float4 A = reinterpret_cast<const float4*>(sp[j])[i];
+          const float4 B = reinterpret_cast<const float4*>(yp[j])[i];
+          const float av[4] = {A.x, A.y, A.z, A.w};
+          const float bv[4] = {B.x, B.y, B.z, B.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[4 + 5 * j + 0] += av[q] * yv[q];
+            acc[4 + 5 * j + 1] += bv[q] * yv[q];
+            acc[4 + 5 * j + 2] += sv[q] * bv[q];
+            acc[4 + 5 * j + 3] += av[q] * gv[q];
+            acc[4 + 5 * j + 4] += bv[q] * gv[q];
+          }
+        }
+      }
+    }
+  }
+  {
+    float (*tile)[kVecThreads] = reinterpret_cast<float (*)[kVecThreads]>(raw);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* o = part + ((int64_t)slice * gridDim.x + blockIdx.x) * kHeadCols;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h) __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kHalf; ++k) tile[k][threadIdx.x] = acc[h * kHalf + k];
+      __syncthreads();
+      // fp32 inside the block (256 per-thread fp32 accumulators per row), double across blocks
+      for (int k = w; k < kHalf; k += kVecThreads / 32) {
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kVecThreads / 32; q += 2) { s0 += tile[k][lane + 32 * q]; s1 += tile[k][lane + 32 * (q + 1)]; }
+        const float sum = warp_sum(s0 + s1);
+        if (lane == 0) o[h * kHalf + k] = (double)sum;
+      }
+    }
+    // the row also carries this block's share of the pending evaluation's loss partials (scatter launch) and of
+    // the pending PH_DIR step's vec partials, so that the epilogue reduces ONE array
+    if (w == 0) {
+      double ls = 0.0;
+      if (want_grad) {
+        for (int j = blockIdx.x + lane * (int)gridDim.x; j < tl.nl; j += 32 * (int)gridDim.x) ls += __ldcg(tl.lpart + j);
+        ls = warp_sum(ls);
+      }
+      if (lane == 0) o[kColLoss] = ls;
+      if (lane < 4) o[kColVec + lane] = (want_grad && prev == PH_DIR) ? __ldcg(vpart + (int64_t)blockIdx.x * 4 + lane) : 0.0;
+    }
+  }
+  if (last_block_done(&S->tickets[0])) step_head_body(S, part, gridDim.x, tl, raw, t, t_entry);
+}
+
+// the vector kernel of a late-epilogue step (see above).  `gz` is the buffer the scatter kernel adds into: g itself
+// on one GPU (zeroed AFTER this thread has read its elements), the peer-visible partial buffer on several.
+__global__ void __launch_bounds__(kVecThreads)
+step_vec_kernel(SolverState* __restrict__ S, const float* g, float* __restrict__ gprev, float* __restrict__ d,
+                float* __restrict__ X, float* __restrict__ xinit, const float* __restrict__ Sb,
+                const float* __restrict__ Yb, int64_t npad, int64_t nvalid, int center_m, float* gz,
+                const Comm* __restrict__ comm, double* __restrict__ vpart) {
+  if (off(&S->active)) return;
+  const int ph = S->phase;  // written by the head kernel's epilogue
+  if (blockIdx.x == 0 && threadIdx.x == 0 && ph == PH_DIR) S->dbg[7] = gtime();
+  const bool mat = ph == PH_MAT, dir = ph == PH_DIR, move = ph != PH_FRESH;
+  if (comm != nullptr && !mat) comm_wait_readers_fwd(comm, &S->error);  // gz is the peer-visible partial buffer
+  const float t = (float)S->t_cur;
+  float mu[4] = {0.f, 0.f, 0.f, 0.f};
+  if (center_m == 1) { float v = S->mu_x[0] + t * S->mu_d[0]; mu[0] = mu[1] = mu[2] = mu[3] = v; }
+  else if (center_m == 2) {
+    float v0 = S->mu_x[0] + t * S->mu_d[0], v1 = S->mu_x[1] + t * S->mu_d[1];
+    mu[0] = mu[2] = v0; mu[1] = mu[3] = v1;
+  } else if (center_m == 4) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mu[c] = S->mu_x[c] + t * S->mu_d[c];
+  }
+  __shared__ float cs[kMaxMemory], cy[kMaxMemory];
+  __shared__ const float* ps[kMaxMemory];
+  __shared__ const float* py[kMaxMemory];
+  const int count = dir ? S->lb.count : 0;
+  const float cg = (float)S->lb.cg;
+  if ((int)threadIdx.x < count) {
+    cs[threadIdx.x] = (float)S->lb.cs[threadIdx.x];
+    cy[threadIdx.x] = (float)S->lb.cy[threadIdx.x];
+    const int q = S->lb.order[threadIdx.x];
+    ps[threadIdx.x] = Sb + (int64_t)q * npad;
+    py[threadIdx.x] = Yb + (int64_t)q * npad;
+  }
+  __syncthreads();
+  double acc[3] = {0.0, 0.0, 0.0};
+  float fa[3] = {0.0f, 0.0f, 0.0f};
+  float mx = 0.0f;
+  int cnt = 0;
+  const int64_t n4 = npad >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + 1; i += stride) {
+    if (move && i < n4) {
+      float4 A, D;
+      if (dir) {
+        const float4 G = reinterpret_cast<const float4*>(g)[i];
+        A = reinterpret_cast<const float4*>(X)[i];
+        float r[4] = {cg * G.x, cg * G.y, cg * G.z, cg * G.w};
+        for (int j = 0; j < count; ++j) {
+          const float4 Sv = reinterpret_cast<const float4*>(ps[j])[i];
+          const float4 Yv = reinterpret_cast<const float4*>(py[j])[i];
+          r[0] += cs[j] * Sv.x + cy[j] * Yv.x; r[1] += cs[j] * Sv.y + cy[j] * Yv.y;
+          r[2] += cs[j] * Sv.z + cy[j] * Yv.z; r[3] += cs[j] * Sv.w + cy[j] * Yv.w;
+        }
+        D = make_float4(r[0], r[1], r[2], r[3]);
+        reinterpret_cast<float4*>(d)[i] = D;
+        reinterpret_cast<float4*>(gprev)[i] = G;
+        reinterpret_cast<float4*>(xinit)[i] = A;
+        fa[0] += G.x * r[0] + G.y * r[1] + G.z * r[2] + G.w * r[3];
+        fa[1] += r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+        fa[2] += A.x * A.x + A.y * A.y + A.z * A.z + A.w * A.w;
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(r[0]), fabsf(r[1])), fmaxf(fabsf(r[2]), fabsf(r[3]))));
+        if (++cnt == 16) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { acc[k] += (double)fa[k]; fa[k] = 0.0f; }
+          cnt = 0;
+        }
+      } else {
+        A = reinterpret_cast<const float4*>(xinit)[i];
+        D = reinterpret_cast<const float4*>(d)[i];
+      }
+      float4 R = make_float4(fmaf(t, D.x, A.x) - mu[0], fmaf(t, D.y, A.y) - mu[1], fmaf(t, D.z, A.z) - mu[2],
+                             fmaf(t, D.w, A.w) - mu[3]);
+      if (center_m != 0 && 4 * i + 3 >= nvalid) {  // keep the zero padding behind the last row
+        if (4 * i + 0 >= nvalid) R.x = 0.f;
+        if (4 * i + 1 >= nvalid) R.y = 0.f;
+        if (4 * i + 2 >= nvalid) R.z = 0.f;
+        if (4 * i + 3 >= nvalid) R.w = 0.f;
+      }
+      reinterpret_cast<float4*>(X)[i] = R;
+    }
+    if (!mat) reinterpret_cast<float4*>(gz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (dir) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] += (double)fa[k];
+    __shared__ double sm[3 * 32];
+    __shared__ float smx[32];
+    block_sum<3>(acc, sm);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m2 = 0.0f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m2 = fmaxf(m2, smx[w]);
+      double* o = vpart + (int64_t)blockIdx.x * 4;
+      o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = (double)m2;
+    }
+  }
+}
+
 // mode 2: (re)arm the solver for iterations up to `limit`
 __global__ void resume_kernel(SolverState* __restrict__ S, int limit) {
   if (threadIdx.x != 0) return;
@@ -1234,13 +1739,17 @@ __global__ void init_state_kernel(SolverState* S, double eps, int memory, int ma
   S->stop_after = 0; S->pad0 = 0; S->eps = eps; S->loss = 0.0; S->gg = 0.0; S->g1 = 0.0; S->gtd = 0.0f;
   S->dmax = 0.0f; S->dd = 0.0; S->xx = 0.0; S->t_last = 0.0; S->t_eval = 0.0; S->func_evals = 0;
   S->max_stats = max_stats; S->world = world;
-  S->paused = 0; S->iter_limit = max_stats; S->pad1 = 0;
+  S->paused = 0; S->iter_limit = max_stats; S->pend = 0;
+  S->t_cur = 0.0;
+  for (int c = 0; c < 4; ++c) { S->cs_g[c] = 0.0; S->cs_d[c] = 0.0; S->mu_x[c] = 0.0f; S->mu_d[c] = 0.0f; }
+  for (int q = 0; q < kSlots; ++q) for (int c = 0; c < 4; ++c) { S->cs_S[q][c] = 0.0; S->cs_Y[q][c] = 0.0; }
   set_phase(S, PH_FRESH);  // mode 2 (sets need_fresh = 1 as well)
   for (int k = 0; k < 4; ++k) S->tickets[k] = 0u;
   S->avg = avg; S->resid = resid; S->pct = pct; S->steplen = steplen;
   lbfgs_reset(S->lb, memory);
   ls_begin(S->ls, 0.0, 0.0, 0.0f, 0.0f);
   S->ls.phase = LS_DONE;
+  fill_head_desc(S);
 }
 
 int vec_blocks(int64_t n4) {
@@ -1262,6 +1771,7 @@ struct mde_solver {
   float *X = nullptr, *xinit = nullptr, *d = nullptr, *g = nullptr, *gprev = nullptr, *Sb = nullptr, *Yb = nullptr;
   float* gpart = nullptr;            // mode 2, multi-GPU: this rank's partial [gradient | loss] before the all-reduce
   double *dpart = nullptr;           // dot partials
+  double *vpart = nullptr;           // late-epilogue steps: (g.d, d.d, X.X, max|d|) partials of the vec kernel
   double *stats = nullptr;           // 4 * max_iter doubles
   void* projws = nullptr;
   ProjWs pw{};
@@ -1294,6 +1804,7 @@ struct mde_solver {
   int unroll = 1;
   // mode 2: flat step graphs (one step / steps_per_graph steps), no conditional nodes
   int steps_per_graph = 8;           // MDE_B200_STEPS (1..64)
+  int late = 0;                      // mode 2: evaluation bookkeeping rides in the next step's head kernel (MDE_B200_LATE=0: off)
   cudaGraph_t step_graph = nullptr, steps_graph = nullptr;
   cudaGraphExec_t step_exec = nullptr, steps_exec = nullptr;
   int step_kernels = 0;              // kernel nodes per step
@@ -1338,11 +1849,11 @@ Tail make_tail(mde_solver* s, int mode) {
   Tail tl;
   tl.fuse = s->fuse; tl.mode = mode;
   tl.lpart = loss_partials_ptr(s->edges); tl.nl = s->nl; tl.tail = s->g + s->npad;
-  tl.p_total = (double)edges_p_total(s->edges); tl.n_rows = s->n; tl.h_while = s->h_while;
+  tl.p_total = (double)edges_p_total(s->edges); tl.n_rows = s->n; tl.inv_n = 1.0 / (double)s->n; tl.h_while = s->h_while;
   return tl;
 }
 
-int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cudaStream_t st) {
+int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cudaStream_t st, bool with_dots = true) {
   // several GPUs: scatter into this rank's partial buffer (peer-visible), then all-reduce into g
   const bool multi = s->opts.world_size > 1;
   const bool staged = multi && s->opts.mode == 2;  // (the peer-memory path exists in mode 2 only)
@@ -1402,6 +1913,7 @@ int enqueue_eval(mde_solver* s, const int* flag, bool zero_g, int tail_mode, cud
       MDE_LAUNCH_CHECK();
     }
   }
+  if (!with_dots) return 0;  // late-epilogue steps: the next step's head kernel computes them
   Tail tl = make_tail(s, tail_mode);
   grad_dots_kernel<<<s->nvb, kVecThreads, 0, st>>>(flag, s->g, s->d, s->npad, s->dpart, s->S, tl);
   MDE_LAUNCH_CHECK();
@@ -1473,12 +1985,25 @@ int enqueue_finish(mde_solver* s, cudaStream_t st) {
 // mode 2: one step (see step_end_body).  Every kernel is gated on the device; the chain has no host decision.
 int enqueue_step(mde_solver* s, cudaStream_t st) {
   SolverState* S = s->S;
-  int rc = enqueue_direction(s, st, &S->g_dir);
-  if (rc) return rc;
-  step_axpy_kernel<<<s->nvb, kVecThreads, 0, st>>>(S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m,
-                                                   s->opts.world_size > 1 ? s->gpart : s->g,
-                                                   s->comm_connected ? s->comm_dev : nullptr);
-  MDE_LAUNCH_CHECK();
+  int rc = 0;
+  if (s->late) {
+    int slices = (s->opts.memory_size + kPairsPerSlice - 1) / kPairsPerSlice;
+    dim3 grid(s->nvb, slices);
+    Tail tl = make_tail(s, 3);
+    step_head_kernel<<<grid, kVecThreads, 0, st>>>(S, s->g, s->gprev, s->d, s->X, s->Sb, s->Yb, s->npad, s->center_m,
+                                                   s->dpart, s->vpart, tl);
+    MDE_LAUNCH_CHECK();
+    step_vec_kernel<<<s->nvb, kVecThreads, 0, st>>>(S, s->g, s->gprev, s->d, s->X, s->xinit, s->Sb, s->Yb, s->npad,
+                                                    s->N, s->center_m, s->opts.world_size > 1 ? s->gpart : s->g,
+                                                    s->comm_connected ? s->comm_dev : nullptr, s->vpart);
+    MDE_LAUNCH_CHECK();
+  } else {
+    if ((rc = enqueue_direction(s, st, &S->g_dir))) return rc;
+    step_axpy_kernel<<<s->nvb, kVecThreads, 0, st>>>(S, s->xinit, s->d, s->X, s->npad, s->N, s->center_m,
+                                                     s->opts.world_size > 1 ? s->gpart : s->g,
+                                                     s->comm_connected ? s->comm_dev : nullptr);
+    MDE_LAUNCH_CHECK();
+  }
   switch (s->opts.constraint) {  // retraction of the moved iterate (project_callback, lbfgs.py:368-372)
     case MDE_CONSTRAINT_CENTERED:
       if (!s->center_m && (rc = enqueue_project_centered(s->X, s->n, s->m, s->pw, &S->g_proj, st))) return rc;
@@ -1497,13 +2022,25 @@ int enqueue_step(mde_solver* s, cudaStream_t st) {
     }
     default: return MDE_E_INVALID;
   }
-  return enqueue_eval(s, &S->g_eval, false, 3, st);
+  return enqueue_eval(s, &S->g_eval, false, 3, st, !s->late);
 }
 
 int build_step_graph(mde_solver* s, int steps, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out) {
 #define GTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
   if (!s->cap_stream) GTRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
   const unsigned long long l0 = g_launch_count;
+  if (s->late && s->nl == 0) {
+    // the head kernel of a step reads the loss partials of the PREVIOUS step's scatter launch: their count is
+    // known once one evaluation has been enqueued, so capture one throw-away step first
+    cudaGraph_t tmp = nullptr;
+    GTRY(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeRelaxed));
+    int rc0 = enqueue_step(s, s->cap_stream);
+    cudaError_t e0 = cudaStreamEndCapture(s->cap_stream, &tmp);
+    if (tmp) cudaGraphDestroy(tmp);
+    if (rc0) return rc0;
+    GTRY(e0);
+    g_launch_count = l0;
+  }
   GTRY(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeRelaxed));
   int rc = 0;
   for (int k = 0; k < steps && !rc; ++k) rc = enqueue_step(s, s->cap_stream);
@@ -1651,7 +2188,9 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   }
   TRY(cudaMalloc(&s->Sb, (int64_t)(opts->memory_size + 1) * s->npad * sizeof(float)));
   TRY(cudaMalloc(&s->Yb, (int64_t)(opts->memory_size + 1) * s->npad * sizeof(float)));
-  TRY(cudaMalloc(&s->dpart, sizeof(double) * (int64_t)kVecBlocks * kDotsPerSlice * kMaxSlices));
+  TRY(cudaMalloc(&s->dpart, sizeof(double) * (int64_t)kVecBlocks * kHeadCols * kMaxSlices));
+  TRY(cudaMalloc(&s->vpart, sizeof(double) * (int64_t)kVecBlocks * 4));
+  TRY(cudaMemsetAsync(s->vpart, 0, sizeof(double) * (int64_t)kVecBlocks * 4, st));
   TRY(cudaMalloc(&s->stats, sizeof(double) * 4 * (int64_t)opts->max_iter));
   TRY(cudaMalloc(&s->projws, mde_project_ws_bytes(n, m)));
   s->pw = proj_ws_carve(s->projws, m);
@@ -1671,7 +2210,12 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
   s->nvb = vec_blocks(s->npad >> 2);
   if (opts->constraint == MDE_CONSTRAINT_CENTERED && (m == 1 || m == 2 || m == 4)) s->center_m = m;
   { const char* ev = getenv("MDE_B200_FUSE"); if (ev && ev[0] == '0') s->fuse = 0; }
-  if (opts->mode == 2) s->fuse = 1;  // the phase machine lives in the fused epilogues
+  if (opts->mode == 2) {
+    s->fuse = 1;  // the phase machine lives in the fused epilogues
+    s->late = 1;
+    const char* ev = getenv("MDE_B200_LATE");
+    if (ev && ev[0] == '0') s->late = 0;
+  }
   if (opts->mode == 2 && opts->world_size == 1) {  // several GPUs: graphs are built by mde_solver_comm_connect
     s->nl = 0;
     TRY(cudaStreamSynchronize(st));
@@ -1711,7 +2255,7 @@ int mde_solver_destroy(mde_solver_t* s) {
   if (!s->comm_region) cudaFree(s->g);  // (several GPUs: g lives inside the peer-visible region)
   for (int q = 0; q < kMaxWorld; ++q) if (s->peer_base[q]) cudaIpcCloseMemHandle(s->peer_base[q]);
   cudaFree(s->comm_region); cudaFree(s->comm_dev);
-  cudaFree(s->Sb); cudaFree(s->Yb); cudaFree(s->dpart); cudaFree(s->stats); cudaFree(s->projws);
+  cudaFree(s->Sb); cudaFree(s->Yb); cudaFree(s->dpart); cudaFree(s->vpart); cudaFree(s->stats); cudaFree(s->projws);
   cudaFree(s->anchors); cudaFree(s->anchor_values);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   if (s->graph) cudaGraphDestroy(s->graph);
@@ -1815,6 +2359,16 @@ int mde_solver_begin_ex(mde_solver_t* s, const float* X0, double eps, int max_it
   return 0;
 }
 
+// globaltimer stamps (ns) of the last late-epilogue head kernel that started an iteration: [0] last block's entry,
+// [1] epilogue entry, [2] state staged, [3] partials reduced, [4] previous step finished, [5] direction done,
+// [6] before write-back, [7] the vec kernel's first block.  Diagnostics only (tools/solver_times.py).
+int mde_solver_debug_times(mde_solver_t* s, unsigned long long* out8, void* stream) {
+  if (!s || !out8) return MDE_E_INVALID;
+  MDE_CUDA_TRY(cudaMemcpyAsync(out8, s->S->dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  MDE_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
 int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, void* stream) {
   if (!s) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1841,16 +2395,16 @@ int mde_solver_run(mde_solver_t* s, int iters, int* iters_done, int* converged, 
       const int spg = s->steps_per_graph;
       if (s->opts.world_size > 1 && !s->steps_exec) {
         // host-hook all-reduce: stream-launched steps; every rank enqueues the same number of steps (same `remaining`: the replicated state machines agree)
-        int n_steps = remaining + remaining / 8 + (round > 0 ? 1 : 0);
+        int n_steps = remaining + remaining / 8 + (round > 0 ? 1 : 0) + s->late;
         if (n_steps > 64) n_steps = 64;
         for (int b = 0; b < n_steps; ++b) { if ((rc = enqueue_step(s, st))) return rc; }
       } else if (remaining >= spg) {
-        int graphs = (remaining + remaining / 8) / spg;
+        int graphs = (remaining + remaining / 8 + s->late) / spg;
         if (graphs * spg > 96) graphs = 96 / spg > 0 ? 96 / spg : 1;  // <= ~96 steps in flight per status read
         for (int b = 0; b < graphs; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->steps_exec, st));
         steps = (long long)graphs * spg;
       } else {
-        const int singles = remaining + remaining / 4 + (round > 0 ? 1 : 0);
+        const int singles = remaining + remaining / 4 + (round > 0 ? 1 : 0) + s->late;
         for (int b = 0; b < singles; ++b) MDE_CUDA_TRY(cudaGraphLaunch(s->step_exec, st));
         steps = singles;
       }

@@ -96,17 +96,21 @@ def _knn_problem(pm, n, k, m, seed, constraint):
     return pm.MDE(n, m, torch.tensor(edges, device="cuda"), f, constraint), edges, w
 
 
-def test_graph_and_hoststep_modes_agree_bitwise():
-    """Both drivers enqueue the same kernels with the same fixed-order reductions; on a problem
-    evaluated without atomics races mattering (tiny, one block) the statistics must be identical."""
+def test_graph_and_hoststep_modes_agree_bitwise(monkeypatch):
+    """The three drivers enqueue the same kernels with the same fixed-order reductions (mode 2 with its
+    pre-"late epilogue" step chain, MDE_B200_LATE=0); on a problem evaluated without atomics races mattering
+    (tiny, one block) the statistics must be identical.  The default mode-2 chain computes g.d, ||g|| and the
+    history dots in one fused pass (different summation order): same trajectory to rounding."""
+    import os
     import pymde_b200 as pm
     from pymde_b200 import optim
-    g = dict(np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "trajectories.npz")))
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "trajectories.npz")))
     res = []
     old = optim.DEFAULT_MODE
     try:
-        for mode in (0, 1, 2):
+        for mode, late in ((0, "0"), (1, "0"), (2, "0"), (2, "1")):
             optim.DEFAULT_MODE = mode
+            monkeypatch.setenv("MDE_B200_LATE", late)
             mde, X0 = build(pm, "docs5", g)
             mde.embed(X=X0, max_iter=30, eps=1e-7)
             res.append((mde.solve_stats.iterations, list(mde.solve_stats.average_distortions)))
@@ -115,6 +119,9 @@ def test_graph_and_hoststep_modes_agree_bitwise():
     assert res[0][0] == res[1][0] == res[2][0]
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-6)
     np.testing.assert_allclose(res[0][1], res[2][1], rtol=1e-6)
+    k = min(10, len(res[3][1]), len(res[0][1]))
+    np.testing.assert_allclose(res[0][1][:k], res[3][1][:k], rtol=1e-4)
+    np.testing.assert_allclose(res[0][1][-1], res[3][1][-1], rtol=1e-2)
 
 
 @pytest.mark.parametrize("cname", ["centered", "standardized"])
