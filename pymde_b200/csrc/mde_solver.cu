@@ -1303,7 +1303,7 @@ __device__ void reduce_head_rows(const double* __restrict__ part, int nb, double
 }
 
 __device__ void step_head_body(SolverState* __restrict__ S, const double* __restrict__ part, int nblocks, Tail tl,
-                               unsigned char* smem, float tpass, unsigned long long t_entry) {
+                               unsigned char* smem, float tpass, int count, unsigned long long t_entry) {
   SolverState* sS = reinterpret_cast<SolverState*>(smem);
   double* sums = reinterpret_cast<double*>(smem + sizeof(SolverState));
   double* dots = sums + kMaxSlices * kHeadCols;
@@ -1311,18 +1311,32 @@ __device__ void step_head_body(SolverState* __restrict__ S, const double* __rest
   __shared__ int s_go, s_dirty;
   __shared__ unsigned long long s_t[8];
   if (threadIdx.x == 0) s_t[0] = gtime();
+  // the state's loads and the partial rows' loads are in flight together (one L2 round trip for both)
+  constexpr int kStagePer = (kStateDoubles + 255) / 256;
+  double stage[kStagePer];
   {
     const double* src = reinterpret_cast<const double*>(S);
-    double* dst = reinterpret_cast<double*>(sS);
-    for (int k = threadIdx.x; k < kStateDoubles; k += blockDim.x) dst[k] = __ldcg(src + k);
+#pragma unroll
+    for (int q = 0; q < kStagePer; ++q) {
+      const int k = (int)threadIdx.x + q * 256;
+      stage[q] = (k < kStateDoubles) ? __ldcg(src + k) : 0.0;
+    }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) s_t[1] = gtime();
-  const int pend = sS->pend, prev = sS->phase, count = sS->lb.count, n_iter = sS->lb.n_iter;
   int slices = (count + kPairsPerSlice - 1) / kPairsPerSlice;
   if (slices < 1) slices = 1;
   for (int sl = 0; sl < slices; ++sl)
     reduce_head_rows(part + (int64_t)sl * nblocks * kHeadCols, nblocks, sums + sl * kHeadCols, kColVec + 3);
+  {
+    double* dst = reinterpret_cast<double*>(sS);
+#pragma unroll
+    for (int q = 0; q < kStagePer; ++q) {
+      const int k = (int)threadIdx.x + q * 256;
+      if (k < kStateDoubles) dst[k] = stage[q];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_t[1] = gtime();
+  const int pend = sS->pend, prev = sS->phase, n_iter = sS->lb.n_iter;
   if (threadIdx.x == 0) {
     s_t[2] = gtime();
     if (pend) {  // ---- finish the previous step ----
@@ -1386,15 +1400,7 @@ __device__ void step_head_body(SolverState* __restrict__ S, const double* __rest
     if (n_iter > 0) lbfgs_direction_block(B, dots, sums[0], sums[1], sums[2], sums[3], flags);
     else lbfgs_direction_block(B, dots, 0.0, 0.0, 0.0, 0.0, flags);
     __syncthreads();
-    if (threadIdx.x == 0) {
-      s_t[4] = gtime();
-      double t0 = 1.0;
-      if (B.n_iter == 1) {  // t = min(1, 1/||g||_1) * lr
-        const float inv = 1.0f / (float)sS->g1;
-        t0 = (inv < 1.0f) ? (double)inv : 1.0;
-      }
-      sS->t_cur = t0;
-    }
+    if (threadIdx.x == 64) s_t[4] = gtime();
     if (threadIdx.x < 32) {
       // column sums of d = cg g + sum_j cs_j S_j + cy_j Y_j from TRACKED column sums of the stored pairs
       // (S_c = t d_prev, Y_c = g - g_prev), lane j owning pair j.  These are rounding-level quantities (the gradient
@@ -1427,14 +1433,28 @@ __device__ void step_head_body(SolverState* __restrict__ S, const double* __rest
       }
     }
   }
-  if (threadIdx.x == 0) {
-    sS->pend = sS->active ? 1 : 0;
-    fill_head_desc(sS);
-    if (s_go) {
-      s_t[5] = gtime();
-      sS->dbg[0] = t_entry;
-      for (int k = 0; k < 6; ++k) sS->dbg[1 + k] = s_t[k];
+  if ((threadIdx.x >> 5) == 1) {
+    // (a different warp than the column sums: both run concurrently) first step length of a new iteration and the
+    // 64-byte descriptor the next head kernel's blocks read
+    const int lane = threadIdx.x & 31;
+    double tc = sS->t_cur;
+    if (s_go && sS->lb.n_iter == 1) {  // t = min(1, 1/||g||_1) * lr
+      const float inv = 1.0f / (float)sS->g1;
+      tc = (inv < 1.0f) ? (double)inv : 1.0;
+    } else if (s_go) tc = 1.0;
+    HeadDesc& h = sS->hd;
+    h.order[lane] = (unsigned char)sS->lb.order[lane];
+    if (lane == 0) {
+      sS->t_cur = tc;
+      sS->pend = sS->active ? 1 : 0;
+      h.pend = sS->pend; h.phase = sS->phase; h.count = sS->lb.count; h.n_iter = sS->lb.n_iter; h.cand = sS->lb.cand;
+      h.t_cur = (float)tc; h.t_last = (float)sS->t_last; h.pad = 0;
     }
+  }
+  if (threadIdx.x == 64 && s_go) {
+    s_t[5] = gtime();
+    sS->dbg[0] = t_entry;
+    for (int k = 0; k < 6; ++k) sS->dbg[1 + k] = s_t[k];
   }
   __syncthreads();
   {
@@ -1451,9 +1471,9 @@ step_head_kernel(SolverState* __restrict__ S, const float* __restrict__ g, const
                  float* __restrict__ Yb, int64_t npad, int mcols, double* __restrict__ part,
                  const double* __restrict__ vpart, Tail tl) {
   if (off(&S->active)) return;
-  constexpr int kHalf = kHeadAcc / 2;
-  __shared__ __align__(16) unsigned char raw[sizeof(float) * kHalf * kVecThreads];
-  static_assert(sizeof(raw) >= kHeadSmemBytes, "scalar epilogue must fit in the reduction tile");
+  __shared__ __align__(16) unsigned char raw[(kHeadSmemBytes + 15) / 16 * 16];  // warp sums, then the scalar stage
+  static_assert(sizeof(raw) >= sizeof(float) * kHeadAcc * (kVecThreads / 32), "warp sums must fit");
+  static_assert(kHeadAcc == 66, "the transposing butterfly below is written for 64 + 2 accumulators");
   __shared__ const float* sp[kPairsPerSlice];
   __shared__ const float* yp[kPairsPerSlice];
   const unsigned long long t_entry = gtime();
@@ -1468,6 +1488,14 @@ step_head_kernel(SolverState* __restrict__ S, const float* __restrict__ g, const
   const bool want_hist = (n_iter0 != 0) && !(pend && prev == PH_FRESH) && (slice == 0 || slice * kPairsPerSlice < count);
   const bool spec = pend && (prev == PH_DIR || prev == PH_TRIAL);
   const float t = spec ? __int_as_float(h1.y) : __int_as_float(h1.z);
+  // warp 7's share of the previous launches' partials: issued now, used after the pass
+  double pre_loss = 0.0, pre_vec = 0.0;
+  if ((threadIdx.x >> 5) == 7 && want_grad) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x + lane * (int)gridDim.x;
+    if (j < tl.nl) pre_loss = __ldcg(tl.lpart + j);
+    if (lane < 4 && prev == PH_DIR) pre_vec = __ldcg(vpart + (int64_t)blockIdx.x * 4 + lane);
+  }
   float acc[kHeadAcc];
 #pragma unroll
   for (int k = 0; k < kHeadAcc; ++k) acc[k] = 0.0f;
@@ -1547,37 +1575,48 @@ step_head_kernel(SolverState* __restrict__ S, const float* __restrict__ g, const
     }
   }
   {
-    float (*tile)[kVecThreads] = reinterpret_cast<float (*)[kVecThreads]>(raw);
+    // Block reduction of the 66 per-thread accumulators.  Warp level: a transposing butterfly -- at the level with
+    // lane distance o a lane keeps half of its values and sends the other half, so 64 values cost 62 shuffles
+    // (a plain butterfly: 320) and lane L ends with the warp totals of accumulators idx(L) and idx(L) + 1.  Block
+    // level: 8 warps through shared memory.  fp32 inside the block (its 256 per-thread partials are fp32 anyway),
+    // double across blocks.  The summation order is fixed.
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float (*wsum)[kHeadAcc] = reinterpret_cast<float (*)[kHeadAcc]>(raw);
+#define MDE_TR_LEVEL(N, O)                                                              \
+    _Pragma("unroll") for (int i = 0; i < (N); ++i) {                                   \
+      const bool hi = (lane & (O)) != 0;                                                \
+      const float a_ = acc[i], b_ = acc[i + (N)];                                       \
+      acc[i] = (hi ? b_ : a_) + __shfl_xor_sync(kFull, hi ? a_ : b_, (O));              \
+    }
+    MDE_TR_LEVEL(32, 16) MDE_TR_LEVEL(16, 8) MDE_TR_LEVEL(8, 4) MDE_TR_LEVEL(4, 2) MDE_TR_LEVEL(2, 1)
+#undef MDE_TR_LEVEL
+    const int idx = ((lane & 16) ? 32 : 0) | ((lane & 8) ? 16 : 0) | ((lane & 4) ? 8 : 0) | ((lane & 2) ? 4 : 0) |
+                    ((lane & 1) ? 2 : 0);
+    const float x64 = warp_sum(acc[64]);
+    wsum[w][idx] = acc[0]; wsum[w][idx + 1] = acc[1];
+    if (lane == 0) { wsum[w][64] = x64; wsum[w][65] = 0.0f; }
+    __syncthreads();
     double* o = part + ((int64_t)slice * gridDim.x + blockIdx.x) * kHeadCols;
+    if (threadIdx.x < kHeadAcc) {
+      float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h) __syncthreads();
-#pragma unroll
-      for (int k = 0; k < kHalf; ++k) tile[k][threadIdx.x] = acc[h * kHalf + k];
-      __syncthreads();
-      // fp32 inside the block (256 per-thread fp32 accumulators per row), double across blocks
-      for (int k = w; k < kHalf; k += kVecThreads / 32) {
-        float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-        for (int q = 0; q < kVecThreads / 32; q += 2) { s0 += tile[k][lane + 32 * q]; s1 += tile[k][lane + 32 * (q + 1)]; }
-        const float sum = warp_sum(s0 + s1);
-        if (lane == 0) o[h * kHalf + k] = (double)sum;
-      }
+      for (int q = 0; q < kVecThreads / 32; q += 2) { s0 += wsum[q][threadIdx.x]; s1 += wsum[q + 1][threadIdx.x]; }
+      o[threadIdx.x] = (double)(s0 + s1);
     }
     // the row also carries this block's share of the pending evaluation's loss partials (scatter launch) and of
-    // the pending PH_DIR step's vec partials, so that the epilogue reduces ONE array
-    if (w == 0) {
-      double ls = 0.0;
+    // the pending PH_DIR step's vec partials (loaded at the top), so that the epilogue reduces ONE array
+    if (w == 7) {
+      double ls = pre_loss;
       if (want_grad) {
-        for (int j = blockIdx.x + lane * (int)gridDim.x; j < tl.nl; j += 32 * (int)gridDim.x) ls += __ldcg(tl.lpart + j);
+        for (int j = blockIdx.x + (lane + 32) * (int)gridDim.x; j < tl.nl; j += 32 * (int)gridDim.x) ls += __ldcg(tl.lpart + j);
         ls = warp_sum(ls);
       }
       if (lane == 0) o[kColLoss] = ls;
-      if (lane < 4) o[kColVec + lane] = (want_grad && prev == PH_DIR) ? __ldcg(vpart + (int64_t)blockIdx.x * 4 + lane) : 0.0;
+      if (lane < 4) o[kColVec + lane] = pre_vec;
+      if (lane == 4) o[kHeadCols - 1] = 0.0;
     }
   }
-  if (last_block_done(&S->tickets[0])) step_head_body(S, part, gridDim.x, tl, raw, t, t_entry);
+  if (last_block_done(&S->tickets[0])) step_head_body(S, part, gridDim.x, tl, raw, t, count, t_entry);
 }
 
 // the vector kernel of a late-epilogue step (see above).  `gz` is the buffer the scatter kernel adds into: g itself
