@@ -19,6 +19,7 @@
 #ifndef MDE_B200_H
 #define MDE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -216,6 +217,21 @@ int mde_solver_set_allreduce(mde_solver_t* s, mde_allreduce_fn fn, void* user);
 #define MDE_IPC_HANDLE_BYTES 64
 int mde_solver_comm_export(mde_solver_t* s, void* handle_out, int64_t handle_bytes);
 int mde_solver_comm_connect(mde_solver_t* s, int rank, const void* handles, int64_t handle_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Problem construction next to the path: exact k-nearest neighbours.
+ * Replaces the neighbour search of pymde/preprocess/data_matrix.py:91-178 (k_nearest_neighbors: scikit-learn brute
+ * force below 10 000 rows, the approximate pynndescent above; a third-party dependency either way).  X is a device
+ * row-major n x d fp32 matrix.  For every row i the k rows nearest to it in Euclidean distance (i itself excluded)
+ * are written to idx_out[i*k .. i*k+k) in ascending distance with their exact fp32 SQUARED distances in d2_out.
+ * Cross terms run on the tensor cores (tcgen05, bf16 hi/lo split, fp32 accumulate in TMEM) with a running
+ * top-32 per row; the 32 candidates are re-ranked with exact fp32 distances, so the result is that of a brute-force
+ * fp32 search (equal-distance ties aside).  1 <= k <= mde_knn_max_k() (24), k <= n - 1.  `ws`: 1024-byte aligned
+ * device scratch of mde_knn_ws_bytes(n, d) bytes.  Asynchronous on `stream`. */
+int mde_knn_max_k(void);
+int mde_knn_ws_bytes(int64_t n, int d, size_t* bytes);
+int mde_knn(const float* X, int64_t n, int d, int k, int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes,
+            void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Problem construction next to the path.
