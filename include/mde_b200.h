@@ -149,10 +149,11 @@ int64_t mde_project_ws_bytes(int64_t n, int m);
 /* _Centered.project_onto_constraint, constraints.py:106-111: X -= column mean. */
 int mde_project_centered(float* X, int64_t n, int m, void* ws, void* stream);
 /* _Standardized.project_onto_constraint, constraints.py:194-195 -> util.py:129-171:
- * de-mean, then sqrt(n) * polar factor, computed as X (X^T X)^(-1/2) via the m x m Gram
- * and a Jacobi eigensolver on device (m <= 32). */
+ * de-mean, then sqrt(n) * polar factor, computed as X (X^T X)^(-1/2) via the m x m Gram: a Jacobi eigensolver in
+ * one warp for m <= 32, a tiled Gram kernel + fp64 Newton-Schulz inverse square root for 32 < m <= 256 (the reference
+ * pins m = 250 in pymde/test_util.py:20-71).  m > 256: MDE_E_UNSUPPORTED. */
 int mde_project_standardized(float* X, int64_t n, int m, void* ws, void* stream);
-/* _Standardized.project_onto_tangent_space, constraints.py:186-192: Z -= (1/n) X (Z^T X). */
+/* _Standardized.project_onto_tangent_space, constraints.py:186-192: Z -= (1/n) X (Z^T X).  m <= 256. */
 int mde_tangent_standardized(const float* X, float* Z, int64_t n, int m, void* ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------

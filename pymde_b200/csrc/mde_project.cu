@@ -393,22 +393,25 @@ int launch_rowmat(const float* X, float* Y, int64_t n, int m, const ProjWs& w, c
 
 namespace mde {
 
+int enqueue_colmean_wide(const float* X, int64_t n, int m, const ProjWs& w, const int* active, cudaStream_t st) {
+  int mpad = 64;
+  while (mpad < m && mpad < kProjThreads) mpad <<= 1;
+  int nrl = kProjThreads / mpad;
+  const int nb = blocks_for_rows(n, nrl * 8);
+  colsum_wide_kernel<<<nb, kProjThreads, 0, st>>>(X, n, m, mpad, w.partials, active);
+  MDE_LAUNCH_CHECK();
+  colmean_finalize_kernel<<<(m + 7) / 8, 256, 0, st>>>(w.partials, nb, n, m, w.mean, active);
+  MDE_LAUNCH_CHECK();
+  return 0;
+}
+
 int enqueue_project_centered(float* X, int64_t n, int m, const ProjWs& w, const int* active, cudaStream_t st) {
   int nb = 0, rc;
   if (m <= kProjMaxM) {
     if ((rc = launch_moments<false>(X, X, n, m, w, active, &nb, st))) return rc;
     proj_finalize_kernel<0><<<1, 256, 0, st>>>(w.partials, nb, n, m, w.mean, w.mat, w.status, active);
     MDE_LAUNCH_CHECK();
-  } else {
-    int mpad = 64;
-    while (mpad < m && mpad < kProjThreads) mpad <<= 1;
-    int nrl = kProjThreads / mpad;
-    nb = blocks_for_rows(n, nrl * 8);
-    colsum_wide_kernel<<<nb, kProjThreads, 0, st>>>(X, n, m, mpad, w.partials, active);
-    MDE_LAUNCH_CHECK();
-    colmean_finalize_kernel<<<(m + 7) / 8, 256, 0, st>>>(w.partials, nb, n, m, w.mean, active);
-    MDE_LAUNCH_CHECK();
-  }
+  } else if ((rc = enqueue_colmean_wide(X, n, m, w, active, st))) return rc;
   int64_t total = n * m;
   int nbb = (int)((total + kProjThreads * 4 - 1) / (kProjThreads * 4));
   if (nbb > kProjBlocks * 4) nbb = kProjBlocks * 4;
@@ -419,6 +422,7 @@ int enqueue_project_centered(float* X, int64_t n, int m, const ProjWs& w, const 
 }
 
 int enqueue_project_standardized(float* X, int64_t n, int m, const ProjWs& w, const int* active, cudaStream_t st) {
+  if (proj_wide(m)) return enqueue_project_standardized_wide(X, n, m, w, active, st);
   if (m > kProjMaxM) return MDE_E_UNSUPPORTED;
   int nb = 0, rc;
   if ((rc = launch_moments<true>(X, X, n, m, w, active, &nb, st))) return rc;
@@ -429,6 +433,7 @@ int enqueue_project_standardized(float* X, int64_t n, int m, const ProjWs& w, co
 
 int enqueue_tangent_standardized(const float* X, float* Z, int64_t n, int m, const ProjWs& w,
                                  const int* active, cudaStream_t st) {
+  if (proj_wide(m)) return enqueue_tangent_standardized_wide(X, Z, n, m, w, active, st);
   if (m > kProjMaxM) return MDE_E_UNSUPPORTED;
   int nb = 0, rc;
   if ((rc = launch_moments<true>(Z, X, n, m, w, active, &nb, st))) return rc;
@@ -453,13 +458,13 @@ int mde_project_centered(float* X, int64_t n, int m, void* ws, void* stream) {
 
 int mde_project_standardized(float* X, int64_t n, int m, void* ws, void* stream) {
   if (!X || !ws || n < 1 || m < 1) return MDE_E_INVALID;
-  if (m > kProjMaxM) return MDE_E_UNSUPPORTED;
+  if (m > kWideMaxM) return MDE_E_UNSUPPORTED;
   return enqueue_project_standardized(X, n, m, proj_ws_carve(ws, m), nullptr, (cudaStream_t)stream);
 }
 
 int mde_tangent_standardized(const float* X, float* Z, int64_t n, int m, void* ws, void* stream) {
   if (!X || !Z || !ws || n < 1 || m < 1) return MDE_E_INVALID;
-  if (m > kProjMaxM) return MDE_E_UNSUPPORTED;
+  if (m > kWideMaxM) return MDE_E_UNSUPPORTED;
   return enqueue_tangent_standardized(X, Z, n, m, proj_ws_carve(ws, m), nullptr, (cudaStream_t)stream);
 }
 

@@ -2185,7 +2185,7 @@ int mde_solver_create(mde_solver_t** out, const mde_edges_t* e, int64_t n, int m
                       void* stream) {
   if (!out || !e || !opts || n < 1 || m < 1) return MDE_E_INVALID;
   if (opts->memory_size < 1 || opts->memory_size > kMaxMemory) return MDE_E_UNSUPPORTED;
-  if (opts->constraint == MDE_CONSTRAINT_STANDARDIZED && m > kProjMaxM) return MDE_E_UNSUPPORTED;
+  if (opts->constraint == MDE_CONSTRAINT_STANDARDIZED && m > kWideMaxM) return MDE_E_UNSUPPORTED;
   if (opts->constraint < 0 || opts->constraint > MDE_CONSTRAINT_ANCHORED) return MDE_E_INVALID;
   if (opts->max_iter < 1) return MDE_E_INVALID;
   if (opts->mode < 0 || opts->mode > 2) return MDE_E_INVALID;

@@ -308,7 +308,7 @@ class MDE(torch.nn.Module):
             return False
         if type(constraint) not in (constraints._Centered, constraints._Standardized, constraints.Anchored):
             return False
-        if isinstance(constraint, constraints._Standardized) and int(self.embedding_dim) > 32:
+        if isinstance(constraint, constraints._Standardized) and int(self.embedding_dim) > 256:
             return False
         m = int(self.embedding_dim)
         if (m % 4 == 0 and m > 1024) or (m % 4 != 0 and m > 512):  # mirrors launch_distortion (mde_edges.cu)

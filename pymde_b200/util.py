@@ -201,8 +201,9 @@ class Workspace(object):
 def proj_standardized(X, demean=False, inplace=False):
     """sqrt(n) * polar factor of X (pymde/util.py:129-171), on the device.
 
-    m <= 32: fused Gram + on-device Jacobi kernels (mde_project_standardized).  Larger m: the
-    same Gram / eigen formulation with the m x m eigenproblem handed to cuSOLVER through torch."""
+    m <= 32: fused Gram + on-device Jacobi kernels; 32 < m <= 256: tiled Gram, Newton-Schulz inverse square root
+    and row kernel (csrc/mde_project_wide.cu) -- both behind mde_project_standardized.  Larger m: the same Gram /
+    eigen formulation with the m x m eigenproblem handed to cuSOLVER through torch."""
     if X.device.type != "cuda":
         raise ValueError("pymde_b200.util.proj_standardized needs a CUDA tensor")
     out = X if inplace else X.detach().clone()
@@ -210,7 +211,7 @@ def proj_standardized(X, demean=False, inplace=False):
         raise ValueError("expected a contiguous float32 tensor")
     n, m = out.shape
     lib = _lib.load()
-    if m <= 32 and demean:
+    if m <= 256 and demean:
         ws = Workspace.get(out.device, lib.mde_project_ws_bytes(n, m))
         _lib.check(lib.mde_project_standardized(out.data_ptr(), n, m, ws.data_ptr(), stream_ptr(out.device)))
         return out

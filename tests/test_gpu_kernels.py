@@ -209,6 +209,33 @@ def test_proj_standardized_invariants_reference_shapes():
     np.testing.assert_allclose((I.T @ I / 5).cpu().numpy(), np.eye(3), atol=1e-4)  # test_optim.py:13-18
 
 
+@pytest.mark.parametrize("n,m", [(500, 33), (3000, 64), (1000, 100), (20000, 128), (1000, 250), (5000, 256)])
+def test_wide_standardized_projection_and_tangent_match_fp64(n, m):
+    """32 < m <= 256 (csrc/mde_project_wide.cu) against the reference formulas in fp64: the retraction is
+    sqrt(n) U V^T of the de-meaned matrix (pymde/util.py:129-171), the tangent projection Z - X (Z^T X) / n
+    (pymde/constraints.py:186-192)."""
+    pm = _pm()
+    g = torch.Generator(device="cuda").manual_seed(n + m)
+    X = torch.randn((n, m), generator=g, device="cuda") * (1.0 + torch.arange(m, device="cuda") / m) + 0.3
+    P = pm.util.proj_standardized(X, demean=True)
+    Xc = X.double() - X.double().mean(0)
+    U, _, Vh = torch.linalg.svd(Xc, full_matrices=False)
+    ref = (n ** 0.5) * U @ Vh
+    np.testing.assert_allclose(P.cpu().numpy(), ref.cpu().numpy(), atol=5e-5, rtol=0)
+    P64 = P.double()
+    np.testing.assert_allclose((P64.T @ P64 / n).cpu().numpy(), np.eye(m), atol=1e-4)
+    np.testing.assert_allclose(P.mean(0).cpu().numpy(), np.zeros(m), atol=1e-5)
+    # a nearly standardized matrix (what the solver retracts at every trial): same check
+    Q = pm.util.proj_standardized(P + 0.01 * torch.randn((n, m), generator=g, device="cuda"), demean=True)
+    Q64 = Q.double()
+    np.testing.assert_allclose((Q64.T @ Q64 / n).cpu().numpy(), np.eye(m), atol=1e-4)
+    # tangent space
+    Z = torch.randn((n, m), generator=g, device="cuda")
+    T = pm.Standardized().project_onto_tangent_space(P, Z, inplace=False)
+    Tref = Z.double() - P64 @ (Z.double().T @ P64) / n
+    np.testing.assert_allclose(T.cpu().numpy(), Tref.cpu().numpy(), atol=2e-5, rtol=1e-5)
+
+
 def _random_problem(n, p, m, rng, push_pull=True):
     i = rng.integers(0, n, 2 * p)
     j = rng.integers(0, n, 2 * p)
