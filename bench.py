@@ -307,10 +307,12 @@ def kernel_roofline(mde, X0d, m, p_local, n, torch, dev, lib, _lib, cold, profil
     b_alg = p_local * 12 + 2 * n * m * 4 + 8
     achieved = b_alg / (k_ms * 1e-3) / 1e9
     kind = int(lib.mde_edges_kind(lay.handle))  # the layout / kernel family the library picked for this workload
-    prof = load_profile("%s:%s" % (profile_key, {0: "soa", 1: "tiles", 2: "pull"}.get(kind, "?")))
+    prof = load_profile("%s:%s" % (profile_key, {0: "soa", 1: "tiles", 2: "pull", 3: "ell"}.get(kind, "?")))
     kernel = {0: "distortion_quad_kernel<m=2, fused, LOG1P|LOG, fast-math> (sorted-SoA layout)",
               1: "distortion_tile_kernel<m=2, fused, LOG1P|LOG, fast-math> (tile-record layout, push)",
-              2: "distortion_pull_kernel<m=2, fused, LOG1P|LOG, fast-math> (pull-record layout)"}.get(kind, "?")
+              2: "distortion_pull_kernel<m=2, fused, LOG1P|LOG, fast-math> (pull-record layout)",
+              3: "distortion_ell_kernel<m=2, fused, LOG1P|LOG, fast-math> (ELL pull records, one lane per owner)"
+              }.get(kind, "?")
     return {"bound": "hbm", "kernel": kernel,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None if prof is None else prof.get("dram_bytes"),

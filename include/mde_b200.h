@@ -100,8 +100,10 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
 int mde_edges_destroy(mde_edges_t* e);
 int64_t mde_edges_count(const mde_edges_t* e);
 /* which layout / kernel family the library chose: 0 = sorted SoA (quad / strided / wide kernels), 1 = tile records
- * (push kernel, shared-memory dst tile), 2 = pull records (directed entries, no shared-memory atomics).
- * MDE_B200_LAYOUT=soa|tiles|pull overrides the choice (A/B measurements). */
+ * (push kernel, shared-memory dst tile), 2 = pull records (directed entries, no shared-memory atomics), 3 = sorted SoA
+ * + ELL pull records (one lane per owner, pymde_b200/csrc/mde_ell.cu: the fused evaluation runs on the ELL kernel,
+ * value-only / per-edge outputs / external coefficients on the SoA kernels).
+ * MDE_B200_LAYOUT=soa|tiles|pull|ell overrides the choice (A/B measurements). */
 int mde_edges_kind(const mde_edges_t* e);
 /* 1 when the layout was created with MDE_B200_DETERMINISTIC=1 (embedding_dim <= 4): gradient contributions are
  * accumulated as 64-bit fixed point (2^-40 resolution), so value AND gradient are bit-reproducible run to run and
@@ -110,6 +112,24 @@ int mde_edges_kind(const mde_edges_t* e);
 int mde_edges_deterministic(const mde_edges_t* e);
 /* bytes of device memory held by the layout */
 int64_t mde_edges_nbytes(const mde_edges_t* e);
+
+/* The ELL pull records (layout kind 3) are built on the host; this is the same builder on HOST arrays, exported so the
+ * CPU tests can decode the records and check the pull sums against the oracle without a device.  src / dst: p canonical
+ * int32 edges, par0: weights; tile_rows_log2 = 0 and max_cta = 0 pick the defaults.  Buffers are malloc'ed, release them
+ * with mde_ell_host_free.  Record format: pymde_b200/csrc/mde_ell.cu. */
+typedef struct mde_ell_host {
+  unsigned char* rec;  /* rec_bytes */
+  uint32_t* rec_off;   /* [nrec + 1], units of 16 bytes */
+  int32_t* bkt_tile;   /* [nbkt] neighbour tile of bucket b */
+  int32_t* bkt_wt0;    /* [nbkt + 1] first record of bucket b */
+  int32_t* cta_wt0;    /* [ncta + 1] record range of CTA c */
+  int32_t* cta_bkt0;   /* [ncta] bucket holding cta_wt0[c] */
+  int64_t rec_bytes, nrec, nslots, nentries, npadded;
+  int32_t nbkt, ncta, tile_rows_log2, reserved;
+} mde_ell_host_t;
+int mde_ell_host_layout(int64_t n_items, int64_t p, int embedding_dim, const int32_t* src, const int32_t* dst,
+                        const float* par0, int push_pull, int tile_rows_log2, int max_cta, mde_ell_host_t* out);
+void mde_ell_host_free(mde_ell_host_t* h);
 
 /* ---------------------------------------------------------------------------------------
  * Fused average distortion: value and gradient in ONE launch.

@@ -33,6 +33,16 @@ class mde_solver_opts_t(C.Structure):
                 ("anchor_values", C.c_void_p), ("world_size", C.c_int32), ("reserved", C.c_int32)]
 
 
+class mde_ell_host_t(C.Structure):
+    """Host copy of the ELL pull records (include/mde_b200.h; CPU tests decode it)."""
+    _fields_ = [("rec", C.POINTER(C.c_ubyte)), ("rec_off", C.POINTER(C.c_uint32)),
+                ("bkt_tile", C.POINTER(C.c_int32)), ("bkt_wt0", C.POINTER(C.c_int32)),
+                ("cta_wt0", C.POINTER(C.c_int32)), ("cta_bkt0", C.POINTER(C.c_int32)),
+                ("rec_bytes", C.c_int64), ("nrec", C.c_int64), ("nslots", C.c_int64), ("nentries", C.c_int64),
+                ("npadded", C.c_int64), ("nbkt", C.c_int32), ("ncta", C.c_int32), ("tile_rows_log2", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/mde_b200.h declares
@@ -49,6 +59,9 @@ SIGNATURES = {
     "mde_edges_nbytes": (C.c_int64, [C.c_void_p]),
     "mde_edges_kind": (C.c_int, [C.c_void_p]),
     "mde_edges_deterministic": (C.c_int, [C.c_void_p]),
+    "mde_ell_host_layout": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_int, C.POINTER(mde_ell_host_t)]),
+    "mde_ell_host_free": (None, [C.POINTER(mde_ell_host_t)]),
     "mde_distortion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mde_edge_outputs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mde_function_eval": (C.c_int, [C.POINTER(mde_fn_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,

@@ -674,12 +674,14 @@ int launch_distortion(const mde_edges* e, const float* X, int m, float* grad, co
 
 // used by the solver: fused launch leaving per-block loss partials in e->loss_partials
 int distortion_fused(const mde_edges* e, const float* X, int m, float* grad, int* nblocks, cudaStream_t st) {
+  if (e->kind == 3 && m == e->m_hint) return ell_launch(e, X, m, grad, nblocks, nullptr, st);
   if (e->kind == 2) return pull_launch(0, e, X, m, grad, nullptr, nblocks, nullptr, st);
   if (e->kind == 1) return tiled_launch(0, e, X, m, grad, nullptr, nblocks, nullptr, st);
   return launch_distortion<0>(e, X, m, grad, nullptr, nblocks, nullptr, st);
 }
 int distortion_fused_flag(const mde_edges* e, const float* X, int m, float* grad, int* nblocks,
                           const int* flag, cudaStream_t st) {
+  if (e->kind == 3 && m == e->m_hint) return ell_launch(e, X, m, grad, nblocks, flag, st);
   if (e->kind == 2) return pull_launch(0, e, X, m, grad, nullptr, nblocks, flag, st);
   if (e->kind == 1) return tiled_launch(0, e, X, m, grad, nullptr, nblocks, flag, st);
   return launch_distortion<0>(e, X, m, grad, nullptr, nblocks, flag, st);
@@ -722,6 +724,7 @@ static int layout_pref() {  // read at every create: A/B runs build both layouts
   if (ev && !strcmp(ev, "soa")) return 1;
   if (ev && !strcmp(ev, "tiles")) return 2;
   if (ev && !strcmp(ev, "pull")) return 3;
+  if (ev && !strcmp(ev, "ell")) return 4;
   return 0;
 }
 
@@ -741,7 +744,7 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
   int rc = 0, pref = 0;
-  bool dense = false;
+  bool dense = false, want_ell = false;
 #define TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = (int)_e; goto fail; } } while (0)
   TRY(cudaMalloc(&e->loss_partials, sizeof(double) * kMaxLossBlocks));
   // Layout choice (measured on B200, profiles/r02_kernels.md): the SM's L1 -> L2 request path (~1 sector request per
@@ -758,7 +761,12 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
       TRY(cudaMalloc(&e->fx, sizeof(long long) * n_items * embedding_dim));
     }
   }
-  if (embedding_dim >= 1 && embedding_dim <= 4 && !par1 && pref != 1 && (pref != 0 || dense)) {
+  // dense graphs: ELL pull records next to the sorted-SoA arrays (C3-shaped: 110 us against 129 us for the flat pull
+  // records, profiles/r02_kernels.md) whenever the ELL builder accepts the shape (n < 2^24, <= 32 neighbour tiles);
+  // MDE_B200_LAYOUT=ell asks for them on any graph
+  want_ell = embedding_dim >= 1 && embedding_dim <= 4 && !par1 && !e->det && (pref == 4 || (pref == 0 && dense)) &&
+             ell_supported(n_items, embedding_dim);
+  if (embedding_dim >= 1 && embedding_dim <= 4 && !par1 && pref != 1 && pref != 4 && (pref != 0 || dense) && !want_ell) {
     if (pref != 2) {  // pull records
       rc = pull_build(e, edges, par0, fn, embedding_dim, st);
       if (rc == 0) { *out = e; return 0; }
@@ -797,6 +805,13 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
     TRY(cudaStreamSynchronize(st));
   }
   cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(vals_out); cudaFree(tmp);
+  keys_in = keys_out = nullptr; vals_in = vals_out = nullptr; tmp = nullptr;
+  if (want_ell) {
+    // ELL pull records next to the sorted-SoA arrays (kind 3); MDE_E_UNSUPPORTED leaves the layout at kind 0
+    rc = ell_build(e, fn, embedding_dim, st);
+    if (rc != 0 && rc != MDE_E_UNSUPPORTED) goto fail;
+    rc = 0;
+  }
   *out = e;
   return 0;
 fail:
@@ -812,6 +827,7 @@ int mde_edges_destroy(mde_edges_t* e) {
   cudaFree(e->loss_partials); cudaFree(e->fx);
   tiled_free(e);
   pull_free(e);
+  ell_free(e);
   delete e;
   return 0;
 }
@@ -826,7 +842,8 @@ int mde_distortion(const mde_edges_t* e, const float* X, int m, float* grad, dou
   if (!e || !X || m < 1) return MDE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int nb = 0, rc;
-  if (e->kind == 2) rc = pull_launch(grad ? 0 : 1, e, X, m, grad, nullptr, &nb, nullptr, st);
+  if (e->kind == 3 && grad && m == e->m_hint) rc = ell_launch(e, X, m, grad, &nb, nullptr, st);
+  else if (e->kind == 2) rc = pull_launch(grad ? 0 : 1, e, X, m, grad, nullptr, &nb, nullptr, st);
   else if (e->kind == 1) rc = tiled_launch(grad ? 0 : 1, e, X, m, grad, nullptr, &nb, nullptr, st);
   else if (grad) rc = launch_distortion<0>(e, X, m, grad, nullptr, &nb, nullptr, st);
   else rc = launch_distortion<1>(e, X, m, nullptr, nullptr, &nb, nullptr, st);

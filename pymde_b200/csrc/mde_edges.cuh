@@ -15,6 +15,9 @@
 //                           so a warp fetches it with a single cp.async.bulk (TMA) into its shared-memory slot.
 //                           perm[nwt * 128] holds the caller position of every slot (-1 for pads).
 //
+//  kind 3  "SoA + ELL"      m <= 4, n < 2^24, <= 32 neighbour tiles: the kind-0 arrays plus the ELL pull records of
+//                           mde_ell.cu (one lane per owner, 12 bytes per edge).
+//
 //  kind 2  "pull records"   m <= 4.  Same buckets, but every edge is stored as two DIRECTED entries (owner,
 //                           neighbour) and a bucket is (owner super-tile, neighbour tile, class); records are
 //                           1040 bytes: fp32 w[128] | u16 owner offset[128] | u16 neighbour offset[128] | header
@@ -52,6 +55,12 @@ struct mde_edges {
   // ---- kind 2 (pull records, mde_pull.cu): same bucket / CTA tables, 1040-byte records of DIRECTED entries ----
   int32_t* wt_tile = nullptr;   // [nwt] neighbour tile of every warp-tile (per-edge outputs)
   int epl = 4;                  // entries per lane per warp-tile (a warp-tile holds 32 * epl entries)
+  // ---- kind 3 (sorted SoA + ELL pull records, mde_ell.cu): the kind-0 arrays above stay valid ----
+  unsigned char* ell_rec = nullptr;   // variable-size records (144 + 192 W bytes)
+  uint32_t* ell_off = nullptr;        // [ell_nrec + 1] record offsets, units of 16 bytes
+  int32_t *ell_bkt_tile = nullptr, *ell_bkt_wt0 = nullptr, *ell_cta_wt0 = nullptr, *ell_cta_bkt0 = nullptr;
+  int64_t ell_nrec = 0;
+  int ell_ncta = 0;
 };
 
 namespace mde {
@@ -79,5 +88,12 @@ int pull_launch(int mode, const mde_edges* e, const float* X, int m, float* grad
                 int* nblocks_out, const int* flag, cudaStream_t st);
 int pull_edge_outputs(const mde_edges* e, const float* X, int m, float* distances, float* distortions,
                       cudaStream_t st);
+
+// ELL pull kernel (mde_ell.cu): fused value + gradient only; everything else runs on the sorted-SoA kernels
+bool ell_supported(int64_t n_items, int embedding_dim);  // shape accepted by the ELL builder (before any allocation)
+int ell_build(mde_edges* e, const mde_fn_t* fn, int embedding_dim, cudaStream_t st);
+void ell_free(mde_edges* e);
+int ell_launch(const mde_edges* e, const float* X, int m, float* grad, int* nblocks_out, const int* flag,
+               cudaStream_t st);
 
 }  // namespace mde
