@@ -58,7 +58,8 @@ struct mde_edges {
   // ---- kind 3 (sorted SoA + ELL pull records, mde_ell.cu): the kind-0 arrays above stay valid ----
   unsigned char* ell_rec = nullptr;   // variable-size records (144 + 192 W bytes)
   uint32_t* ell_off = nullptr;        // [ell_nrec + 1] record offsets, units of 16 bytes
-  int32_t *ell_bkt_tile = nullptr, *ell_bkt_wt0 = nullptr, *ell_cta_wt0 = nullptr, *ell_cta_bkt0 = nullptr;
+  int32_t *ell_bkt_tile = nullptr, *ell_bkt_wt0 = nullptr;
+  int32_t* ell_cta_desc = nullptr;    // [ell_ncta] int4: first record, end record, first bucket, its neighbour tile
   int64_t ell_nrec = 0;
   int ell_ncta = 0;
 };

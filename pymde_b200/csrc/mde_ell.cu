@@ -8,10 +8,11 @@
 //   * vertices are cut into neighbour tiles of R = 2^rb rows (64 KB of X, resident in shared memory);
 //   * the entries of one (neighbour tile, class, owner) group are cut into LANE-SLOTS of at most 8 entries;
 //     the lane-slots of a (tile, class) are sorted by length and packed 32 at a time into one RECORD:
-//         int32 W, cls, nslots, 0 | u32 owner word[32] | W/2 x ( float2 w[32] | u32 neighbour pair[32] )
+//         int32 W, cls, K, nslots | u32 owner word[K][32] | K x W/2 x ( float2 w[32] | u32 neighbour pair[32] )
 //     (owner word: row | count << 24 | duplicate << 31; neighbour pair: two u16 BYTE offsets of the neighbour rows
-//     inside the tile; 144 + 192 W bytes, W even <= 8; column-major, so lane l reads word l of every column:
-//     conflict-free).  6 bytes per directed entry = 12 bytes per edge, the size of the
+//     inside the tile; W even <= 8; K = 4 / 2 / 1 lane-slots PER LANE for W = 2 / 4 / >= 6, so that short lane-slots
+//     do not pay the per-record work alone; 16 + K (128 + 192 W) bytes; column-major, so lane l reads word l of every
+//     column: conflict-free).  6 bytes per directed entry = 12 bytes per edge, the size of the
 //     sorted-SoA stream;
 //   * ONE LANE owns one lane-slot: it loads its owner row once (LDG through L1), walks its W entries (two LDS for a
 //     pair of entries + one LDS gather of the neighbour row each), keeps the gradient sum of the owner in registers
@@ -43,10 +44,18 @@ namespace {
 constexpr int kEllWarps = 32;
 constexpr int kEllThreads = kEllWarps * 32;
 constexpr int kEllWmax = 8;                                            // entries per lane-slot
-constexpr int kEllHdr = 16 + 128;                                      // header + owner words
 constexpr int kEllPair = 256 + 128;                                    // one column pair: float2 w[32] | u32 idx[32]
-constexpr int kEllSlotBytes = kEllHdr + (kEllWmax / 2) * kEllPair;     // 1680
+__host__ __device__ constexpr int ell_kmax(int W) { return W <= 2 ? 4 : (W <= 4 ? 2 : 1); }  // lane-slots per lane
+__host__ __device__ constexpr int ell_rec_bytes(int W, int K) { return 16 + K * (128 + (W / 2) * kEllPair); }
+constexpr int kEllSlotBytes = ell_rec_bytes(2, 4);                     // 2064: the largest record (W 8, K 1: 1680)
+static_assert(ell_rec_bytes(4, 2) <= kEllSlotBytes && ell_rec_bytes(8, 1) <= kEllSlotBytes &&
+              ell_rec_bytes(6, 1) <= kEllSlotBytes, "slot size");
 constexpr uint32_t kOwnMask = 0x00ffffffu;
+
+int ell_pack_enabled() {  // MDE_B200_ELL_PACK=0: one lane-slot per lane in every record (A/B)
+  const char* e = getenv("MDE_B200_ELL_PACK");
+  return !(e && e[0] == '0');
+}
 
 struct EllHost {
   std::vector<unsigned char> rec;
@@ -122,32 +131,40 @@ int ell_build_host(int64_t n, int64_t p, int m, const int32_t* src, const int32_
         out.bkt_wt0.push_back((int32_t)(out.rec_off.size() - 1));
         tile_open = true;
       }
-      for (size_t i0 = 0; i0 < sorted.size(); i0 += 32) {
-        const int ns = (int)std::min<size_t>(32, sorted.size() - i0);
+      const int pack = ell_pack_enabled();
+      for (size_t i0 = 0; i0 < sorted.size();) {
         const int W = (sorted[i0].len + 1) & ~1;
-        const size_t bytes = (size_t)kEllHdr + (size_t)(W / 2) * kEllPair;
+        const size_t left = sorted.size() - i0;
+        const int K = (int)std::min<size_t>(pack ? ell_kmax(W) : 1, (left + 31) / 32);
+        const int ns = (int)std::min<size_t>((size_t)32 * K, left);
+        const size_t bytes = (size_t)ell_rec_bytes(W, K);
         const size_t off = out.rec.size();
         out.rec.resize(off + bytes, 0);
         unsigned char* r = out.rec.data() + off;
-        int32_t hdr[4] = {W, (int32_t)c, ns, 0};
+        int32_t hdr[4] = {W, (int32_t)c, K, ns};
         memcpy(r, hdr, 16);
         uint32_t* ow = reinterpret_cast<uint32_t*>(r + 16);
-        for (int l = 0; l < 32; ++l) {
-          const bool dup = l >= ns;
-          const Slot& s = sorted[i0 + (dup ? 0 : l)];
-          ow[l] = s.own | (dup ? 0x80000000u : ((uint32_t)s.len << 24));
+        unsigned char* cols = r + 16 + 128 * K;
+        for (int i = 0; i < 32 * K; ++i) {
+          const int k = i / 32, l = i % 32;
+          const bool dup = i >= ns;
+          const Slot& s = sorted[i0 + (dup ? 0 : i)];
+          ow[i] = s.own | (dup ? 0x80000000u : ((uint32_t)s.len << 24));
+          unsigned char* cb = cols + (size_t)k * (W / 2) * kEllPair;
           for (int e = 0; e < W; ++e) {
             const bool real = !dup && e < (int)s.len;
             const uint32_t src_e = s.first + (uint32_t)std::min<int>(e, (int)s.len - 1);
-            float* wp = reinterpret_cast<float*>(r + kEllHdr + (e / 2) * kEllPair) + 2 * l + (e & 1);
-            uint16_t* ip = reinterpret_cast<uint16_t*>(r + kEllHdr + (e / 2) * kEllPair + 256) + 2 * l + (e & 1);
+            float* wp = reinterpret_cast<float*>(cb + (e / 2) * kEllPair) + 2 * l + (e & 1);
+            uint16_t* ip = reinterpret_cast<uint16_t*>(cb + (e / 2) * kEllPair + 256) + 2 * l + (e & 1);
             *wp = real ? ew[src_e] : 0.0f;
             *ip = ej[src_e];
           }
         }
-        out.npadded += 32ll * W;
-        rec_cost.push_back(90 + (int64_t)W * (c ? 31 : 23));  // warp instructions (ncu source page, C2)
+        out.npadded += 32ll * K * W;
+        // warp instructions (ncu source page, C2): per record, per lane-slot row, per entry column
+        rec_cost.push_back(60 + (int64_t)K * (30 + (int64_t)W * (c ? 31 : 23)));
         out.rec_off.push_back((uint32_t)(out.rec.size() / 16));
+        i0 += (size_t)ns;
       }
     }
   }
@@ -199,8 +216,7 @@ struct EllArgs {
   const uint32_t* rec_off;
   const int32_t* bkt_tile;
   const int32_t* bkt_wt0;
-  const int32_t* cta_wt0;
-  const int32_t* cta_bkt0;
+  const int4* cta_desc;  // per CTA: first record, end record, first bucket, neighbour tile of that bucket
   const float* X;
   float* grad;
   double* loss_partials;
@@ -304,11 +320,11 @@ __device__ __forceinline__ void ell_entry(const EllArgs& a, const float* __restr
 
 // all W entries of this lane's lane-slot, straight from the shared-memory slot
 template <int M, int FA, int FR, bool FAST, int CLS>
-__device__ __forceinline__ void ell_columns(const EllArgs& a, const float* __restrict__ Xt, const unsigned char* rec,
+__device__ __forceinline__ void ell_columns(const EllArgs& a, const float* __restrict__ Xt, const unsigned char* cols,
                                             int lane, int W, int cnt, const float (&xi)[M], float (&acc)[M],
                                             float& lf) {
-  const float2* wp = reinterpret_cast<const float2*>(rec + kEllHdr) + lane;
-  const uint32_t* ip = reinterpret_cast<const uint32_t*>(rec + kEllHdr + 256) + lane;
+  const float2* wp = reinterpret_cast<const float2*>(cols) + lane;
+  const uint32_t* ip = reinterpret_cast<const uint32_t*>(cols + 256) + lane;
 #pragma unroll 2
   for (int c2 = 0; 2 * c2 < W; ++c2) {
     const float2 w2 = wp[c2 * (kEllPair / 8)];
@@ -331,8 +347,9 @@ distortion_ell_kernel(const EllArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x;
-  const int wt0 = __ldg(a.cta_wt0 + c), wt1 = __ldg(a.cta_wt0 + c + 1);
-  int bkt = __ldg(a.cta_bkt0 + c);
+  const int4 dsc = __ldg(a.cta_desc + c);  // ONE dependent load before the first copies can be issued
+  const int wt0 = dsc.x, wt1 = dsc.y;
+  int bkt = dsc.z;
 
   if (threadIdx.x == 0) {
 #pragma unroll 1
@@ -354,45 +371,55 @@ distortion_ell_kernel(const EllArgs a) {
     mbar_expect_tx(bar, bytes);
     bulk_g2s_hint(my_slot0 + (uint32_t)s * kEllSlotBytes, a.rec + ((size_t)o0 << 4), bytes, bar, pol);
   };
+  int tile = -1, seg_end = wt0;
+  bool tile_pending = false;
+
+  // CTA-wide: request neighbour tile `tl` (thread 0: bulk copies; everybody: the unaligned tail) / wait for it
+  auto tile_issue = [&](int tl) {
+    tile = tl;
+    const int64_t base = (int64_t)tile << a.rb;
+    const int64_t rows_l = a.n - base;
+    const int rows = (int)(rows_l < (int64_t)R ? rows_l : (int64_t)R);
+    const int nfl = rows * M;
+    const float* xsrc = a.X + base * M;
+    const uint32_t bytes = a.x_vec_ok ? (((uint32_t)nfl * 4u) & ~15u) : 0u;
+    if (threadIdx.x == 0 && bytes > 0) {
+      fence_proxy_async();
+      mbar_expect_tx(x_bar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t chunk = (bytes - off) < 32768u ? (bytes - off) : 32768u;
+        bulk_g2s(smem_u32(Xt) + off, reinterpret_cast<const unsigned char*>(xsrc) + off, chunk, x_bar);
+      }
+    }
+    for (int i = (int)(bytes >> 2) + threadIdx.x; i < nfl; i += kEllThreads) Xt[i] = __ldg(xsrc + i);
+    tile_pending = true;
+    return bytes;
+  };
+  uint32_t tile_bytes = 0;
+  auto tile_wait = [&]() {
+    __syncthreads();  // the plain-load tail of every thread
+    if (tile_bytes > 0) { mbar_wait(x_bar, xph); xph ^= 1; }
+    tile_pending = false;
+  };
+  // the tile of the first bucket is requested NOW: its copy overlaps the record-offset loads and the first record copies
+  if (wt0 < wt1) tile_bytes = tile_issue(dsc.w);
+
   int t = wt0 + warp;
   if (lane == 0) {
     if (t < wt1) issue(__ldg(a.rec_off + t), __ldg(a.rec_off + t + 1), 0);
     if (t + kEllWarps < wt1) issue(__ldg(a.rec_off + t + kEllWarps), __ldg(a.rec_off + t + kEllWarps + 1), 1);
   }
 
-  int tile = -1, seg_end = wt0;
-  int64_t base = 0;
-
-  // CTA-wide: make the neighbour tile of bucket `bkt` resident (same number of barriers for all warps)
+  // make the neighbour tile of bucket `bkt` resident (same number of barriers for all warps)
   auto enter_bucket = [&]() {
     const int new_tile = __ldg(a.bkt_tile + bkt);
     const int be = __ldg(a.bkt_wt0 + bkt + 1);
     seg_end = be < wt1 ? be : wt1;
-    if (new_tile == tile) return;
-    __syncthreads();  // every warp is done reading the old tile
-    tile = new_tile;
-    base = (int64_t)tile << a.rb;
-    const int64_t rows_l = a.n - base;
-    const int rows = (int)(rows_l < (int64_t)R ? rows_l : (int64_t)R);
-    const int nfl = rows * M;
-    const float* xsrc = a.X + base * M;
-    if (a.x_vec_ok) {
-      const uint32_t bytes = ((uint32_t)nfl * 4u) & ~15u;
-      if (threadIdx.x == 0 && bytes > 0) {
-        fence_proxy_async();
-        mbar_expect_tx(x_bar, bytes);
-        for (uint32_t off = 0; off < bytes; off += 32768u) {
-          const uint32_t chunk = (bytes - off) < 32768u ? (bytes - off) : 32768u;
-          bulk_g2s(smem_u32(Xt) + off, reinterpret_cast<const unsigned char*>(xsrc) + off, chunk, x_bar);
-        }
-      }
-      for (int i = (int)(bytes >> 2) + threadIdx.x; i < nfl; i += kEllThreads) Xt[i] = __ldg(xsrc + i);
-      __syncthreads();
-      if (bytes > 0) { mbar_wait(x_bar, xph); xph ^= 1; }
-    } else {
-      for (int i = threadIdx.x; i < nfl; i += kEllThreads) Xt[i] = __ldg(xsrc + i);
-      __syncthreads();
+    if (new_tile != tile) {
+      __syncthreads();  // every warp is done reading the old tile
+      tile_bytes = tile_issue(new_tile);
     }
+    if (tile_pending) tile_wait();
   };
 
   const float c_att = 1.5f * a.inv_p;
@@ -414,26 +441,34 @@ distortion_ell_kernel(const EllArgs a) {
     mbar_wait(my_bar0 + 8u * (uint32_t)s, (phbits >> s) & 1u);
     phbits ^= 1u << s;
     const unsigned char* rec = my_slots + (size_t)s * kEllSlotBytes;
-    const int2 hdr = *reinterpret_cast<const int2*>(rec);  // W, class (broadcast)
-    const uint32_t ow = reinterpret_cast<const uint32_t*>(rec + 16)[lane];
-    const uint32_t own = ow & kOwnMask;
-    const int cnt = (int)((ow >> 24) & 0x7fu);
-    float xi[M], acc[M];
-    e_ldg_row<M>(a.X, own, xi);
+    const int4 hdr = *reinterpret_cast<const int4*>(rec);  // W, class, K, nslots (broadcast)
+    const int W = hdr.x, K = hdr.z;
+    const unsigned char* cols = rec + 16 + 128 * K;
+    const int row_bytes = (W >> 1) * kEllPair;
+    float lrec = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {  // K lane-slots per lane (warp-uniform)
+      const uint32_t ow = reinterpret_cast<const uint32_t*>(rec + 16)[k * 32 + lane];
+      const uint32_t own = ow & kOwnMask;
+      const int cnt = (int)((ow >> 24) & 0x7fu);
+      float xi[M], acc[M];
+      e_ldg_row<M>(a.X, own, xi);
 #pragma unroll
-    for (int q = 0; q < M; ++q) acc[q] = 0.0f;
-    float lf = 0.0f;
-    if (FAST) {
-      if (hdr.y == 0) ell_columns<M, FA, FR, true, 0>(a, Xt, rec, lane, hdr.x, cnt, xi, acc, lf);
-      else ell_columns<M, FA, FR, true, 1>(a, Xt, rec, lane, hdr.x, cnt, xi, acc, lf);
-      const float cc = hdr.y == 0 ? c_att : a.inv_p;  // the class constant of f'/(p d), once per lane-slot
+      for (int q = 0; q < M; ++q) acc[q] = 0.0f;
+      float lf = 0.0f;
+      if (FAST) {
+        if (hdr.y == 0) ell_columns<M, FA, FR, true, 0>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
+        else ell_columns<M, FA, FR, true, 1>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
+        const float cc = hdr.y == 0 ? c_att : a.inv_p;  // the class constant of f'/(p d), once per lane-slot
 #pragma unroll
-      for (int q = 0; q < M; ++q) acc[q] *= cc;
-    } else {
-      ell_columns<M, FA, FR, false, 2>(a, Xt, rec, lane, hdr.x, cnt, xi, acc, lf);
+        for (int q = 0; q < M; ++q) acc[q] *= cc;
+      } else {
+        ell_columns<M, FA, FR, false, 2>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
+      }
+      if (!(ow >> 31)) e_red_row<M>(a.grad, own, acc);
+      lrec += lf;
     }
-    if (!(ow >> 31)) e_red_row<M>(a.grad, own, acc);
-    lsum += (double)lf;
+    lsum += (double)lrec;
     // every lane's loads of this slot have returned (their consumers above have issued): refill it
     __syncwarp();
     if (lane == 0 && t2 < wt1) issue(o0, o1, s);
@@ -501,9 +536,9 @@ namespace mde {
 
 void ell_free(mde_edges* e) {
   cudaFree(e->ell_rec); cudaFree(e->ell_off); cudaFree(e->ell_bkt_tile); cudaFree(e->ell_bkt_wt0);
-  cudaFree(e->ell_cta_wt0); cudaFree(e->ell_cta_bkt0);
+  cudaFree(e->ell_cta_desc);
   e->ell_rec = nullptr; e->ell_off = nullptr; e->ell_bkt_tile = nullptr; e->ell_bkt_wt0 = nullptr;
-  e->ell_cta_wt0 = nullptr; e->ell_cta_bkt0 = nullptr;
+  e->ell_cta_desc = nullptr;
 }
 
 bool ell_supported(int64_t n, int m) {
@@ -546,8 +581,12 @@ int ell_build(mde_edges* e, const mde_fn_t* fn, int m, cudaStream_t st) {
   UP(e->ell_off, h.rec_off, uint32_t);
   UP(e->ell_bkt_tile, h.bkt_tile, int32_t);
   UP(e->ell_bkt_wt0, h.bkt_wt0, int32_t);
-  UP(e->ell_cta_wt0, h.cta_wt0, int32_t);
-  UP(e->ell_cta_bkt0, h.cta_bkt0, int32_t);
+  std::vector<int32_t> desc((size_t)4 * h.ncta);
+  for (int c = 0; c < h.ncta; ++c) {
+    desc[4 * c] = h.cta_wt0[c]; desc[4 * c + 1] = h.cta_wt0[c + 1]; desc[4 * c + 2] = h.cta_bkt0[c];
+    desc[4 * c + 3] = h.bkt_tile[(size_t)h.cta_bkt0[c]];
+  }
+  UP(e->ell_cta_desc, desc, int32_t);
 #undef UP
   cudaError_t se = cudaStreamSynchronize(st);  // the host vectors die with this frame
   if (se != cudaSuccess) { ell_free(e); return (int)se; }
@@ -562,7 +601,7 @@ int ell_launch(const mde_edges* e, const float* X, int m, float* grad, int* nblo
   const size_t smem = ell_smem_bytes(e->rb, m);
   EllArgs a;
   a.rec = e->ell_rec; a.rec_off = e->ell_off; a.bkt_tile = e->ell_bkt_tile; a.bkt_wt0 = e->ell_bkt_wt0;
-  a.cta_wt0 = e->ell_cta_wt0; a.cta_bkt0 = e->ell_cta_bkt0; a.X = X; a.grad = grad;
+  a.cta_desc = reinterpret_cast<const int4*>(e->ell_cta_desc); a.X = X; a.grad = grad;
   a.loss_partials = e->loss_partials; a.flag = flag; a.fn = e->fn; a.inv_p = 1.0f / (float)e->p_total;
   a.n = e->n; a.rb = e->rb;
   a.x_vec_ok = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) ? 1 : 0;

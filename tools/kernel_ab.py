@@ -23,7 +23,7 @@ try:
 except Exception:
     pass
 SHORT = {"RB": "MDE_B200_TILE_RB", "STILE": "MDE_B200_STILE_MB", "MIN": "MDE_B200_TILE_MIN", "SC": "MDE_B200_TILE_SCATTER", "EPL": "MDE_B200_PULL_EPL",
-         "REP": "MDE_B200_PULL_REP"}
+         "REP": "MDE_B200_PULL_REP", "PACK": "MDE_B200_ELL_PACK"}
 flush = None
 
 
