@@ -128,6 +128,8 @@ def test_c3_shape_huber_standardized_2e7_edges():
     X = pm.Standardized().project_onto_constraint(X, inplace=True)
     spec = O.FnSpec(O.L_HUBER, delta.cpu().numpy(), (0.5, 0, 0))
     _check_against_oracle(mde, X, e.cpu().numpy(), spec)
+    from pymde_b200 import _lib
+    assert _lib.load().mde_edges_kind(mde._layout().handle) == 3  # dense graph: sorted SoA + ELL pull records
     mde.embed(X=X, max_iter=6, eps=0.0)  # the device solver runs at this size (Gram + Jacobi retraction)
     st = mde.solve_stats
     assert st.iterations == 6 and st.average_distortions[-1] < st.average_distortions[0]
