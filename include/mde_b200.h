@@ -129,6 +129,11 @@ typedef struct mde_ell_host {
 } mde_ell_host_t;
 int mde_ell_host_layout(int64_t n_items, int64_t p, int embedding_dim, const int32_t* src, const int32_t* dst,
                         const float* par0, int push_pull, int tile_rows_log2, int max_cta, mde_ell_host_t* out);
+/* The builder the library itself uses: same layout, bit for bit, from DEVICE arrays (radix sorts + scans + one fill
+ * kernel); the result is copied back into host buffers (GPU tests compare it with mde_ell_host_layout). */
+int mde_ell_device_layout(int64_t n_items, int64_t p, int embedding_dim, const int32_t* src, const int32_t* dst,
+                          const float* par0, int push_pull, int tile_rows_log2, int max_cta, mde_ell_host_t* out,
+                          void* stream);
 void mde_ell_host_free(mde_ell_host_t* h);
 
 /* ---------------------------------------------------------------------------------------

@@ -61,6 +61,8 @@ SIGNATURES = {
     "mde_edges_deterministic": (C.c_int, [C.c_void_p]),
     "mde_ell_host_layout": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(mde_ell_host_t)]),
+    "mde_ell_device_layout": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_int, C.c_int, C.POINTER(mde_ell_host_t), C.c_void_p]),
     "mde_ell_host_free": (None, [C.POINTER(mde_ell_host_t)]),
     "mde_distortion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mde_edge_outputs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -29,6 +29,7 @@
 // same function is exported for the CPU tests (mde_ell_host_layout), which decode the records and compare the pull
 // sums with the oracle.  The sorted-SoA layout stays alongside (kind 3 = SoA + ELL): value-only evaluation, per-edge
 // outputs and external coefficients run on the SoA kernels.
+#include <cub/cub.cuh>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -57,119 +58,63 @@ int ell_pack_enabled() {  // MDE_B200_ELL_PACK=0: one lane-slot per lane in ever
   return !(e && e[0] == '0');
 }
 
-struct EllHost {
-  std::vector<unsigned char> rec;
-  std::vector<uint32_t> rec_off;  // [nrec + 1], units of 16 bytes
+// Record directory: everything about the records except their bytes.  Derived from the HISTOGRAM of lane-slot lengths
+// per (tile, class) alone -- lane-slots are consumed longest first inside a (tile, class) -- so the host builder and
+// the device builder (which only brings that histogram back to the host) share it and produce identical layouts.
+struct EllPlan {
+  std::vector<uint32_t> rec_off;    // [nrec + 1], units of 16 bytes
+  std::vector<int32_t> rec_hdr;     // [nrec * 4]: W, class, K, lane-slots held
+  std::vector<int32_t> rec_slot0;   // [nrec] first lane-slot of the record in the globally sorted lane-slot order
   std::vector<int32_t> bkt_tile, bkt_wt0, cta_wt0, cta_bkt0;
-  int rb = 0, ncta = 0;
-  int64_t nrec = 0, nslots = 0, nentries = 0, npadded = 0;
+  int ncta = 0;
+  int64_t nrec = 0, nslots = 0, npadded = 0, rec_bytes = 0;
 };
 
-// Pure host code.  src/dst/par0: p canonical edges in any order.  Returns 0 or MDE_E_UNSUPPORTED.
-int ell_build_host(int64_t n, int64_t p, int m, const int32_t* src, const int32_t* dst, const float* par0,
-                   int push_pull, int rb, int max_cta, EllHost& out) {
-  if (m < 1 || m > 4 || n < 1 || p < 1 || n >= (1ll << 24) || p >= (1ll << 29)) return MDE_E_UNSUPPORTED;
-  if (rb < 8 || rb > 15) return MDE_E_UNSUPPORTED;
-  const int64_t R = 1ll << rb;
-  const int64_t ndt = (n + R - 1) >> rb;
-  if (ndt > 32) return MDE_E_UNSUPPORTED;
-  const int64_t row_bytes = 4ll * m;
-  if ((R - 1) * row_bytes > 65535) return MDE_E_UNSUPPORTED;  // neighbour rows are addressed by u16 byte offsets
-  const int64_t ng = ndt * 2 * n;  // groups (tile, class, owner)
-  std::vector<uint32_t> start((size_t)ng + 1, 0u);
-  auto cls_of = [&](int64_t k) -> int64_t { return (push_pull && !(par0[k] >= 0.0f)) ? 1 : 0; };
-  for (int64_t k = 0; k < p; ++k) {
-    const int64_t s = src[k], d = dst[k], c = cls_of(k);
-    if (s < 0 || d < 0 || s >= n || d >= n) return MDE_E_INVALID;
-    ++start[(size_t)((((d >> rb) * 2 + c) * n) + s) + 1];
-    ++start[(size_t)((((s >> rb) * 2 + c) * n) + d) + 1];
-  }
-  for (int64_t g = 0; g < ng; ++g) start[(size_t)g + 1] += start[(size_t)g];
-  const int64_t p2 = 2 * p;
-  std::vector<float> ew((size_t)p2);
-  std::vector<uint16_t> ej((size_t)p2);
-  {
-    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
-    for (int64_t k = 0; k < p; ++k) {
-      const int64_t s = src[k], d = dst[k], c = cls_of(k);
-      uint32_t& f1 = fill[(size_t)((((d >> rb) * 2 + c) * n) + s)];
-      ew[f1] = par0[k]; ej[f1] = (uint16_t)((d & (R - 1)) * row_bytes); ++f1;
-      uint32_t& f2 = fill[(size_t)((((s >> rb) * 2 + c) * n) + d)];
-      ew[f2] = par0[k]; ej[f2] = (uint16_t)((s & (R - 1)) * row_bytes); ++f2;
-    }
-  }
-  struct Slot { uint32_t first; uint32_t own; uint8_t len; };
-  std::vector<Slot> slots, sorted;
+// hist[(tile * 2 + cls) * 9 + len]: lane-slots of length len (1..8) in (tile, cls)
+int ell_plan(const uint32_t* hist, int64_t ndt, int max_cta, EllPlan& out) {
+  const int pack = ell_pack_enabled();
   std::vector<int64_t> rec_cost;
-  out.rec.clear(); out.rec_off.assign(1, 0u);
-  out.bkt_tile.clear(); out.bkt_wt0.clear();
-  out.rb = rb; out.nslots = 0; out.nentries = p2; out.npadded = 0;
+  out.rec_off.assign(1, 0u);
+  out.rec_hdr.clear(); out.rec_slot0.clear(); out.bkt_tile.clear(); out.bkt_wt0.clear();
+  out.nslots = 0; out.npadded = 0;
+  int64_t bytes_total = 0, slot_base = 0;
   for (int64_t tile = 0; tile < ndt; ++tile) {
     bool tile_open = false;
     for (int64_t c = 0; c < 2; ++c) {
-      const int64_t g0 = (tile * 2 + c) * n;
-      slots.clear();
-      for (int64_t own = 0; own < n; ++own) {
-        uint32_t a = start[(size_t)(g0 + own)];
-        const uint32_t b = start[(size_t)(g0 + own) + 1];
-        while (a < b) {
-          const uint32_t len = std::min<uint32_t>(kEllWmax, b - a);
-          slots.push_back({a, (uint32_t)own, (uint8_t)len});
-          a += len;
-        }
-      }
-      if (slots.empty()) continue;
-      // stable counting sort by length, longest first (owners stay ascending inside one length)
-      size_t cnt[kEllWmax + 2] = {0};
-      for (const Slot& s : slots) ++cnt[kEllWmax - s.len + 1];
-      for (int i = 0; i <= kEllWmax; ++i) cnt[i + 1] += cnt[i];
-      sorted.resize(slots.size());
-      for (const Slot& s : slots) sorted[cnt[kEllWmax - s.len]++] = s;
-      out.nslots += (int64_t)sorted.size();
+      const uint32_t* h = hist + (tile * 2 + c) * 9;
+      int64_t total = 0;
+      for (int l = 1; l <= kEllWmax; ++l) total += h[l];
+      if (total == 0) continue;
       if (!tile_open) {
         out.bkt_tile.push_back((int32_t)tile);
         out.bkt_wt0.push_back((int32_t)(out.rec_off.size() - 1));
         tile_open = true;
       }
-      const int pack = ell_pack_enabled();
-      for (size_t i0 = 0; i0 < sorted.size();) {
-        const int W = (sorted[i0].len + 1) & ~1;
-        const size_t left = sorted.size() - i0;
-        const int K = (int)std::min<size_t>(pack ? ell_kmax(W) : 1, (left + 31) / 32);
-        const int ns = (int)std::min<size_t>((size_t)32 * K, left);
-        const size_t bytes = (size_t)ell_rec_bytes(W, K);
-        const size_t off = out.rec.size();
-        out.rec.resize(off + bytes, 0);
-        unsigned char* r = out.rec.data() + off;
-        int32_t hdr[4] = {W, (int32_t)c, K, ns};
-        memcpy(r, hdr, 16);
-        uint32_t* ow = reinterpret_cast<uint32_t*>(r + 16);
-        unsigned char* cols = r + 16 + 128 * K;
-        for (int i = 0; i < 32 * K; ++i) {
-          const int k = i / 32, l = i % 32;
-          const bool dup = i >= ns;
-          const Slot& s = sorted[i0 + (dup ? 0 : i)];
-          ow[i] = s.own | (dup ? 0x80000000u : ((uint32_t)s.len << 24));
-          unsigned char* cb = cols + (size_t)k * (W / 2) * kEllPair;
-          for (int e = 0; e < W; ++e) {
-            const bool real = !dup && e < (int)s.len;
-            const uint32_t src_e = s.first + (uint32_t)std::min<int>(e, (int)s.len - 1);
-            float* wp = reinterpret_cast<float*>(cb + (e / 2) * kEllPair) + 2 * l + (e & 1);
-            uint16_t* ip = reinterpret_cast<uint16_t*>(cb + (e / 2) * kEllPair + 256) + 2 * l + (e & 1);
-            *wp = real ? ew[src_e] : 0.0f;
-            *ip = ej[src_e];
-          }
-        }
+      // length of the lane-slot at position i0 of the (longest first) order
+      int len = kEllWmax;
+      int64_t upto = h[kEllWmax];  // lane-slots with length >= len
+      for (int64_t i0 = 0; i0 < total;) {
+        while (i0 >= upto) { --len; upto += h[len]; }
+        const int W = (len + 1) & ~1;
+        const int64_t left = total - i0;
+        const int K = (int)std::min<int64_t>(pack ? ell_kmax(W) : 1, (left + 31) / 32);
+        const int ns = (int)std::min<int64_t>(32ll * K, left);
+        out.rec_hdr.push_back(W); out.rec_hdr.push_back((int32_t)c); out.rec_hdr.push_back(K); out.rec_hdr.push_back(ns);
+        out.rec_slot0.push_back((int32_t)(slot_base + i0));
+        bytes_total += ell_rec_bytes(W, K);
+        out.rec_off.push_back((uint32_t)(bytes_total / 16));
         out.npadded += 32ll * K * W;
         // warp instructions (ncu source page, C2): per record, per lane-slot row, per entry column
         rec_cost.push_back(60 + (int64_t)K * (30 + (int64_t)W * (c ? 31 : 23)));
-        out.rec_off.push_back((uint32_t)(out.rec.size() / 16));
-        i0 += (size_t)ns;
+        i0 += ns;
       }
+      slot_base += total;
     }
   }
+  out.nslots = slot_base;
   out.nrec = (int64_t)out.rec_off.size() - 1;
-  if (out.nrec < 1 || out.rec.size() >= (1ull << 35)) return MDE_E_UNSUPPORTED;
+  out.rec_bytes = bytes_total;
+  if (out.nrec < 1 || bytes_total >= (1ll << 35) || slot_base >= (1ll << 31)) return MDE_E_UNSUPPORTED;
   out.bkt_wt0.push_back((int32_t)out.nrec);
   // persistent grid: contiguous record ranges of equal estimated cost; every tile a CTA has to load (its first one
   // and one per bucket boundary inside its range) is charged like kTileCost warp instructions
@@ -204,6 +149,110 @@ int ell_build_host(int64_t n, int64_t p, int m, const int32_t* src, const int32_
     int b = (int)(it - out.bkt_wt0.begin()) - 1;
     const int nb = (int)out.bkt_tile.size();
     out.cta_bkt0[c] = b < 0 ? 0 : (b >= nb ? nb - 1 : b);
+  }
+  return 0;
+}
+
+int ell_check_shape(int64_t n, int64_t p, int m, int rb) {
+  if (m < 1 || m > 4 || n < 1 || p < 1 || n >= (1ll << 24) || p >= (1ll << 29)) return MDE_E_UNSUPPORTED;
+  if (rb < 8 || rb > 15) return MDE_E_UNSUPPORTED;
+  const int64_t R = 1ll << rb;
+  if (((n + R - 1) >> rb) > 32) return MDE_E_UNSUPPORTED;
+  if ((R - 1) * 4ll * m > 65535) return MDE_E_UNSUPPORTED;  // neighbour rows are addressed by u16 byte offsets
+  return 0;
+}
+
+struct EllHost {
+  std::vector<unsigned char> rec;
+  EllPlan plan;
+  int rb = 0;
+  int64_t nentries = 0;
+};
+
+// Pure host code (CPU tests; MDE_B200_ELL_BUILD=host).  src/dst/par0: p canonical edges in any order.
+int ell_build_host(int64_t n, int64_t p, int m, const int32_t* src, const int32_t* dst, const float* par0,
+                   int push_pull, int rb, int max_cta, EllHost& out) {
+  int rc = ell_check_shape(n, p, m, rb);
+  if (rc) return rc;
+  const int64_t R = 1ll << rb;
+  const int64_t ndt = (n + R - 1) >> rb;
+  const int64_t row_bytes = 4ll * m;
+  const int64_t ng = ndt * 2 * n;  // groups (tile, class, owner)
+  std::vector<uint32_t> start((size_t)ng + 1, 0u);
+  auto cls_of = [&](int64_t k) -> int64_t { return (push_pull && !(par0[k] >= 0.0f)) ? 1 : 0; };
+  for (int64_t k = 0; k < p; ++k) {
+    const int64_t s = src[k], d = dst[k], c = cls_of(k);
+    if (s < 0 || d < 0 || s >= n || d >= n) return MDE_E_INVALID;
+    ++start[(size_t)((((d >> rb) * 2 + c) * n) + s) + 1];
+    ++start[(size_t)((((s >> rb) * 2 + c) * n) + d) + 1];
+  }
+  for (int64_t g = 0; g < ng; ++g) start[(size_t)g + 1] += start[(size_t)g];
+  const int64_t p2 = 2 * p;
+  std::vector<float> ew((size_t)p2);
+  std::vector<uint16_t> ej((size_t)p2);
+  {
+    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+    for (int64_t k = 0; k < p; ++k) {
+      const int64_t s = src[k], d = dst[k], c = cls_of(k);
+      uint32_t& f1 = fill[(size_t)((((d >> rb) * 2 + c) * n) + s)];
+      ew[f1] = par0[k]; ej[f1] = (uint16_t)((d & (R - 1)) * row_bytes); ++f1;
+      uint32_t& f2 = fill[(size_t)((((s >> rb) * 2 + c) * n) + d)];
+      ew[f2] = par0[k]; ej[f2] = (uint16_t)((s & (R - 1)) * row_bytes); ++f2;
+    }
+  }
+  // lane-slots in (tile, class, owner, piece) order, then stably sorted by (tile, class, longest first)
+  struct Slot { uint32_t first; uint32_t own; uint8_t len; };
+  std::vector<Slot> sorted;
+  std::vector<uint32_t> hist((size_t)ndt * 2 * 9, 0u);
+  {
+    std::vector<Slot> slots;
+    for (int64_t tc = 0; tc < ndt * 2; ++tc) {
+      slots.clear();
+      for (int64_t own = 0; own < n; ++own) {
+        uint32_t a = start[(size_t)(tc * n + own)];
+        const uint32_t b = start[(size_t)(tc * n + own) + 1];
+        while (a < b) {
+          const uint32_t len = std::min<uint32_t>(kEllWmax, b - a);
+          slots.push_back({a, (uint32_t)own, (uint8_t)len});
+          ++hist[(size_t)tc * 9 + len];
+          a += len;
+        }
+      }
+      size_t cnt[kEllWmax + 2] = {0};
+      for (const Slot& sl : slots) ++cnt[kEllWmax - sl.len + 1];
+      for (int i = 0; i <= kEllWmax; ++i) cnt[i + 1] += cnt[i];
+      const size_t base = sorted.size();
+      sorted.resize(base + slots.size());
+      for (const Slot& sl : slots) sorted[base + cnt[kEllWmax - sl.len]++] = sl;
+    }
+  }
+  rc = ell_plan(hist.data(), ndt, max_cta, out.plan);
+  if (rc) return rc;
+  const EllPlan& pl = out.plan;
+  out.rb = rb; out.nentries = p2;
+  out.rec.assign((size_t)pl.rec_bytes, 0);
+  for (int64_t t = 0; t < pl.nrec; ++t) {
+    const int W = pl.rec_hdr[4 * t], K = pl.rec_hdr[4 * t + 2], ns = pl.rec_hdr[4 * t + 3];
+    unsigned char* r = out.rec.data() + ((size_t)pl.rec_off[(size_t)t] << 4);
+    memcpy(r, &pl.rec_hdr[4 * t], 16);
+    uint32_t* ow = reinterpret_cast<uint32_t*>(r + 16);
+    unsigned char* cols = r + 16 + 128 * K;
+    const size_t i0 = (size_t)pl.rec_slot0[(size_t)t];
+    for (int i = 0; i < 32 * K; ++i) {
+      const int k = i / 32, l = i % 32;
+      const bool dup = i >= ns;
+      const Slot& sl = sorted[i0 + (dup ? 0 : i)];
+      ow[i] = sl.own | (dup ? 0x80000000u : ((uint32_t)sl.len << 24));
+      unsigned char* cb = cols + (size_t)k * (W / 2) * kEllPair;
+      for (int e = 0; e < W; ++e) {
+        const bool real = !dup && e < (int)sl.len;
+        const uint32_t src_e = sl.first + (uint32_t)std::min<int>(e, (int)sl.len - 1);
+        float* wp = reinterpret_cast<float*>(cb + (e / 2) * kEllPair) + 2 * l + (e & 1);
+        uint16_t* ip = reinterpret_cast<uint16_t*>(cb + (e / 2) * kEllPair + 256) + 2 * l + (e & 1);
+        *wp = real ? ew[src_e] : 0.0f;
+        *ip = ej[src_e];
+      }
+    }
   }
   return 0;
 }
@@ -549,49 +598,260 @@ bool ell_supported(int64_t n, int m) {
   return ((n + R - 1) >> rb) <= 32 && (R - 1) * 4 * m <= 65535 && ell_smem_bytes(rb, m) <= 227u * 1024u;
 }
 
-// Called on a finished sorted-SoA layout (kind 0): copies src / dst / par0 to the host, builds the ELL records there and
-// uploads them; on success the layout becomes kind 3.  Returns 0, MDE_E_UNSUPPORTED (layout stays kind 0) or an error.
+// ------------------------------------------------------------------------------------------
+// device builder: the same layout as ell_build_host, bit for bit, from device-resident src / dst / par0
+//   1. key = (neighbour tile, class, owner) of the 2p directed entries + a histogram of the groups
+//   2. stable radix sort of the entry ids by key (edge order survives inside a group, like the host's counting sort)
+//   3. scan of the group counts, lane-slots of <= 8 entries per group, histogram of their lengths per (tile, class)
+//   4. stable radix sort of the lane-slots by (tile, class, longest first)
+//   5. the 9-bin histograms go to the host, ell_plan lays the records out, one block per record fills it
+// ------------------------------------------------------------------------------------------
+struct EllDev {
+  unsigned char* rec = nullptr;
+  EllPlan plan;
+  int rb = 0;
+  int64_t nentries = 0;
+};
+
+}  // namespace mde
+namespace {
+
+__global__ void ell_keys_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                const float* __restrict__ par0, int push_pull, int64_t p2, int64_t n, int rb,
+                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ gcount) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p2) return;
+  const int64_t e = k >> 1;
+  const int s = src[e], d = dst[e];
+  const int own = (k & 1) ? d : s, nbr = (k & 1) ? s : d;
+  const uint32_t cls = (push_pull && !(par0[e] >= 0.0f)) ? 1u : 0u;
+  const uint32_t key = (uint32_t)((((int64_t)(nbr >> rb) * 2 + cls) * n) + own);
+  keys[k] = key;
+  vals[k] = (uint32_t)k;
+  atomicAdd(gcount + key, 1u);
+}
+
+__global__ void ell_group_slots_kernel(const uint32_t* __restrict__ gcount, int64_t ng, uint32_t* __restrict__ gslots) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ng) gslots[g] = (gcount[g] + (uint32_t)kEllWmax - 1u) / (uint32_t)kEllWmax;
+}
+
+// one thread per group: its lane-slots (first entry, owner, length), their sort key and the length histogram
+__global__ void ell_slots_kernel(const uint32_t* __restrict__ gcount, const uint32_t* __restrict__ gstart,
+                                 const uint32_t* __restrict__ gslot0, int64_t ng, int64_t n,
+                                 uint32_t* __restrict__ slot_first, uint32_t* __restrict__ slot_ownlen,
+                                 uint32_t* __restrict__ skey, uint32_t* __restrict__ sval, uint32_t* __restrict__ shist) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  const uint32_t c = gcount[g];
+  if (c == 0) return;
+  const uint32_t tc = (uint32_t)(g / n), own = (uint32_t)(g % n);
+  uint32_t a = gstart[g], j = gslot0[g];
+  for (uint32_t left = c; left > 0; ++j) {
+    const uint32_t len = left < (uint32_t)kEllWmax ? left : (uint32_t)kEllWmax;
+    slot_first[j] = a;
+    slot_ownlen[j] = own | (len << 24);
+    skey[j] = tc * 8u + ((uint32_t)kEllWmax - len);
+    sval[j] = j;
+    atomicAdd(shist + tc * 9u + len, 1u);
+    a += len;
+    left -= len;
+  }
+}
+
+// one block per record, one thread per lane-slot position
+__global__ void ell_fill_kernel(const uint32_t* __restrict__ rec_off, const int32_t* __restrict__ rec_hdr,
+                                const int32_t* __restrict__ rec_slot0, const uint32_t* __restrict__ sorted_slot,
+                                const uint32_t* __restrict__ slot_first, const uint32_t* __restrict__ slot_ownlen,
+                                const uint32_t* __restrict__ sorted_entry, const int32_t* __restrict__ src,
+                                const int32_t* __restrict__ dst, const float* __restrict__ par0, int rb, int row_bytes,
+                                unsigned char* __restrict__ rec) {
+  const int64_t t = blockIdx.x;
+  const int W = rec_hdr[4 * t], K = rec_hdr[4 * t + 2], ns = rec_hdr[4 * t + 3];
+  unsigned char* r = rec + ((size_t)rec_off[t] << 4);
+  const int i = threadIdx.x;
+  if (i < 4) reinterpret_cast<int32_t*>(r)[i] = rec_hdr[4 * t + i];
+  if (i >= 32 * K) return;
+  const int k = i >> 5, l = i & 31;
+  const bool dup = i >= ns;
+  const uint32_t sidx = sorted_slot[(int64_t)rec_slot0[t] + (dup ? 0 : i)];
+  const uint32_t first = slot_first[sidx], ol = slot_ownlen[sidx];
+  const int len = (int)(ol >> 24);
+  reinterpret_cast<uint32_t*>(r + 16)[i] = (ol & kOwnMask) | (dup ? 0x80000000u : ((uint32_t)len << 24));
+  unsigned char* cb = r + 16 + 128 * K + (size_t)k * (W / 2) * kEllPair;
+  const uint32_t rmask = (1u << rb) - 1u;
+  for (int e = 0; e < W; ++e) {
+    const bool real = !dup && e < len;
+    const uint32_t id = sorted_entry[first + (uint32_t)(e < len ? e : len - 1)];
+    const uint32_t edge = id >> 1;
+    const int nbr = (id & 1u) ? src[edge] : dst[edge];
+    reinterpret_cast<float*>(cb + (e / 2) * kEllPair)[2 * l + (e & 1)] = real ? par0[edge] : 0.0f;
+    reinterpret_cast<uint16_t*>(cb + (e / 2) * kEllPair + 256)[2 * l + (e & 1)] =
+        (uint16_t)(((uint32_t)nbr & rmask) * (uint32_t)row_bytes);
+  }
+}
+
+int ebits_for(uint64_t maxval) {
+  int b = 1;
+  while (b < 64 && (maxval >> b) != 0) ++b;
+  return b;
+}
+
+}  // namespace
+namespace mde {
+
+int ell_build_device(int64_t n, int64_t p, int m, const int32_t* src, const int32_t* dst, const float* par0,
+                     int push_pull, int rb, int max_cta, EllDev& out, cudaStream_t st) {
+  int rc = ell_check_shape(n, p, m, rb);
+  if (rc) return rc;
+  const int64_t R = 1ll << rb, ndt = (n + R - 1) >> rb, ng = ndt * 2 * n, p2 = 2 * p;
+  const int nh = (int)(ndt * 2 * 9);
+  uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
+  uint32_t *gcount = nullptr, *gstart = nullptr, *gslots = nullptr, *gslot0 = nullptr;
+  uint32_t *slot_first = nullptr, *slot_ownlen = nullptr, *skey = nullptr, *sval = nullptr, *skey_o = nullptr,
+           *sval_o = nullptr, *shist = nullptr, *d_off = nullptr;
+  int32_t *d_hdr = nullptr, *d_slot0 = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0, need = 0;
+  std::vector<uint32_t> hist((size_t)nh, 0u);
+  uint32_t tail[2] = {0, 0};
+  int64_t nslots = 0;
+  const int tb = 256;
+#define TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = (int)_e; goto done; } } while (0)
+  TRY(cudaMalloc(&keys_in, 4 * p2)); TRY(cudaMalloc(&keys_out, 4 * p2));
+  TRY(cudaMalloc(&vals_in, 4 * p2)); TRY(cudaMalloc(&vals_out, 4 * p2));
+  TRY(cudaMalloc(&gcount, 4 * ng)); TRY(cudaMalloc(&gstart, 4 * ng));
+  TRY(cudaMalloc(&gslots, 4 * ng)); TRY(cudaMalloc(&gslot0, 4 * ng));
+  TRY(cudaMalloc(&shist, 4 * nh));
+  TRY(cudaMemsetAsync(gcount, 0, 4 * ng, st));
+  TRY(cudaMemsetAsync(shist, 0, 4 * nh, st));
+  ell_keys_kernel<<<ceil_div_i64(p2, tb), tb, 0, st>>>(src, dst, par0, push_pull, p2, n, rb, keys_in, vals_in, gcount);
+  ++g_launch_count;
+  TRY(cudaPeekAtLastError());
+  // workspace: the largest of the four CUB calls
+  TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, keys_in, keys_out, vals_in, vals_out, (int)p2, 0, ebits_for((uint64_t)ng), st));
+  tmp_bytes = need;
+  TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, gcount, gstart, (int)ng, st));
+  tmp_bytes = std::max(tmp_bytes, need);
+  TRY(cudaMalloc(&tmp, tmp_bytes));
+  need = tmp_bytes;
+  TRY(cub::DeviceRadixSort::SortPairs(tmp, need, keys_in, keys_out, vals_in, vals_out, (int)p2, 0, ebits_for((uint64_t)ng), st));
+  need = tmp_bytes;
+  TRY(cub::DeviceScan::ExclusiveSum(tmp, need, gcount, gstart, (int)ng, st));
+  ell_group_slots_kernel<<<ceil_div_i64(ng, tb), tb, 0, st>>>(gcount, ng, gslots);
+  ++g_launch_count;
+  TRY(cudaPeekAtLastError());
+  need = tmp_bytes;
+  TRY(cub::DeviceScan::ExclusiveSum(tmp, need, gslots, gslot0, (int)ng, st));
+  TRY(cudaMemcpyAsync(&tail[0], gslot0 + (ng - 1), 4, cudaMemcpyDeviceToHost, st));
+  TRY(cudaMemcpyAsync(&tail[1], gslots + (ng - 1), 4, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
+  nslots = (int64_t)tail[0] + (int64_t)tail[1];
+  if (nslots < 1 || nslots >= (1ll << 31)) { rc = MDE_E_UNSUPPORTED; goto done; }
+  TRY(cudaMalloc(&slot_first, 4 * nslots)); TRY(cudaMalloc(&slot_ownlen, 4 * nslots));
+  TRY(cudaMalloc(&skey, 4 * nslots)); TRY(cudaMalloc(&sval, 4 * nslots));
+  TRY(cudaMalloc(&skey_o, 4 * nslots)); TRY(cudaMalloc(&sval_o, 4 * nslots));
+  ell_slots_kernel<<<ceil_div_i64(ng, tb), tb, 0, st>>>(gcount, gstart, gslot0, ng, n, slot_first, slot_ownlen, skey, sval, shist);
+  ++g_launch_count;
+  TRY(cudaPeekAtLastError());
+  {
+    size_t need2 = 0;
+    const int sbits = ebits_for((uint64_t)(ndt * 2 * 8));
+    TRY(cub::DeviceRadixSort::SortPairs(nullptr, need2, skey, skey_o, sval, sval_o, (int)nslots, 0, sbits, st));
+    if (need2 > tmp_bytes) { cudaFree(tmp); tmp = nullptr; TRY(cudaMalloc(&tmp, need2)); tmp_bytes = need2; }
+    need2 = tmp_bytes;
+    TRY(cub::DeviceRadixSort::SortPairs(tmp, need2, skey, skey_o, sval, sval_o, (int)nslots, 0, sbits, st));
+  }
+  TRY(cudaMemcpyAsync(hist.data(), shist, 4 * nh, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
+  rc = ell_plan(hist.data(), ndt, max_cta, out.plan);
+  if (rc) goto done;
+  if (out.plan.nslots != nslots) { rc = MDE_E_INVALID; goto done; }
+  {
+    const EllPlan& pl = out.plan;
+    TRY(cudaMalloc(&out.rec, (size_t)pl.rec_bytes));
+    TRY(cudaMalloc(&d_off, 4 * (pl.nrec + 1)));
+    TRY(cudaMalloc(&d_hdr, 16 * pl.nrec));
+    TRY(cudaMalloc(&d_slot0, 4 * pl.nrec));
+    TRY(cudaMemcpyAsync(d_off, pl.rec_off.data(), 4 * (pl.nrec + 1), cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(d_hdr, pl.rec_hdr.data(), 16 * pl.nrec, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(d_slot0, pl.rec_slot0.data(), 4 * pl.nrec, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemsetAsync(out.rec, 0, (size_t)pl.rec_bytes, st));
+    ell_fill_kernel<<<(unsigned)pl.nrec, 128, 0, st>>>(d_off, d_hdr, d_slot0, sval_o, slot_first, slot_ownlen, vals_out, src,
+                                                       dst, par0, rb, 4 * m, out.rec);
+    ++g_launch_count;
+    TRY(cudaPeekAtLastError());
+    TRY(cudaStreamSynchronize(st));
+    out.rb = rb; out.nentries = p2;
+  }
+done:
+  cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(vals_out); cudaFree(gcount); cudaFree(gstart);
+  cudaFree(gslots); cudaFree(gslot0); cudaFree(slot_first); cudaFree(slot_ownlen); cudaFree(skey); cudaFree(sval);
+  cudaFree(skey_o); cudaFree(sval_o); cudaFree(shist); cudaFree(d_off); cudaFree(d_hdr); cudaFree(d_slot0); cudaFree(tmp);
+  if (rc != 0) { cudaFree(out.rec); out.rec = nullptr; }
+  return rc;
+#undef TRY
+}
+
+// Called on a finished sorted-SoA layout (kind 0): builds the ELL records from its src / dst / par0 on the device
+// (MDE_B200_ELL_BUILD=host: copies them to the host and runs ell_build_host, the builder the CPU tests cover; both give the
+// same bytes); on success the layout becomes kind 3.  Returns 0, MDE_E_UNSUPPORTED (layout stays kind 0) or an error.
 int ell_build(mde_edges* e, const mde_fn_t* fn, int m, cudaStream_t st) {
   if (e->kind != 0 || e->has_par1 || e->det || m < 1 || m > 4) return MDE_E_UNSUPPORTED;
   int rb = ell_default_rb(m);
   { const int r = eenv_int("MDE_B200_TILE_RB", 0); if (r >= 8 && r <= 15) rb = r; }
   if (ell_smem_bytes(rb, m) > 227u * 1024u) return MDE_E_UNSUPPORTED;
   const int64_t p = e->p, n = e->n;
-  if (n >= (1ll << 24) || ((n + (1ll << rb) - 1) >> rb) > 32) return MDE_E_UNSUPPORTED;
-  std::vector<int32_t> hs((size_t)p), hd((size_t)p);
-  std::vector<float> hw((size_t)p);
-  MDE_CUDA_TRY(cudaMemcpyAsync(hs.data(), e->src, sizeof(int32_t) * p, cudaMemcpyDeviceToHost, st));
-  MDE_CUDA_TRY(cudaMemcpyAsync(hd.data(), e->dst, sizeof(int32_t) * p, cudaMemcpyDeviceToHost, st));
-  MDE_CUDA_TRY(cudaMemcpyAsync(hw.data(), e->par0, sizeof(float) * p, cudaMemcpyDeviceToHost, st));
-  MDE_CUDA_TRY(cudaStreamSynchronize(st));
-  EllHost h;
-  int rc = ell_build_host(n, p, m, hs.data(), hd.data(), hw.data(), fn->push_pull, rb, kNumSMs, h);
+  int rc = ell_check_shape(n, p, m, rb);
   if (rc) return rc;
   const void* k = eselect_kernel(e->fn, m);
   if (!k) return MDE_E_UNSUPPORTED;
   if ((rc = econfigure_kernel(k))) return rc;
-  const int nbkt = (int)h.bkt_tile.size();
+  const char* bev = getenv("MDE_B200_ELL_BUILD");
+  const bool on_host = bev && !strcmp(bev, "host");
+  EllHost h;
+  EllDev d;
+  const EllPlan* pl = nullptr;
+  if (on_host) {
+    std::vector<int32_t> hs((size_t)p), hd((size_t)p);
+    std::vector<float> hw((size_t)p);
+    MDE_CUDA_TRY(cudaMemcpyAsync(hs.data(), e->src, sizeof(int32_t) * p, cudaMemcpyDeviceToHost, st));
+    MDE_CUDA_TRY(cudaMemcpyAsync(hd.data(), e->dst, sizeof(int32_t) * p, cudaMemcpyDeviceToHost, st));
+    MDE_CUDA_TRY(cudaMemcpyAsync(hw.data(), e->par0, sizeof(float) * p, cudaMemcpyDeviceToHost, st));
+    MDE_CUDA_TRY(cudaStreamSynchronize(st));
+    rc = ell_build_host(n, p, m, hs.data(), hd.data(), hw.data(), fn->push_pull, rb, kNumSMs, h);
+    if (rc) return rc;
+    pl = &h.plan;
+    cudaError_t ce = cudaMalloc(&e->ell_rec, h.rec.size());
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->ell_rec, h.rec.data(), h.rec.size(), cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) { ell_free(e); return (int)ce; }
+  } else {
+    rc = ell_build_device(n, p, m, e->src, e->dst, e->par0, fn->push_pull, rb, kNumSMs, d, st);
+    if (rc) return rc;
+    pl = &d.plan;
+    e->ell_rec = d.rec;
+  }
+  const int nbkt = (int)pl->bkt_tile.size();
 #define UP(dst, vec, T)                                                                              \
   do {                                                                                               \
     cudaError_t _e = cudaMalloc(&(dst), sizeof(T) * (vec).size());                                   \
     if (_e == cudaSuccess) _e = cudaMemcpyAsync((dst), (vec).data(), sizeof(T) * (vec).size(), cudaMemcpyHostToDevice, st); \
     if (_e != cudaSuccess) { ell_free(e); return (int)_e; }                                          \
   } while (0)
-  UP(e->ell_rec, h.rec, unsigned char);
-  UP(e->ell_off, h.rec_off, uint32_t);
-  UP(e->ell_bkt_tile, h.bkt_tile, int32_t);
-  UP(e->ell_bkt_wt0, h.bkt_wt0, int32_t);
-  std::vector<int32_t> desc((size_t)4 * h.ncta);
-  for (int c = 0; c < h.ncta; ++c) {
-    desc[4 * c] = h.cta_wt0[c]; desc[4 * c + 1] = h.cta_wt0[c + 1]; desc[4 * c + 2] = h.cta_bkt0[c];
-    desc[4 * c + 3] = h.bkt_tile[(size_t)h.cta_bkt0[c]];
+  UP(e->ell_off, pl->rec_off, uint32_t);
+  UP(e->ell_bkt_tile, pl->bkt_tile, int32_t);
+  UP(e->ell_bkt_wt0, pl->bkt_wt0, int32_t);
+  std::vector<int32_t> desc((size_t)4 * pl->ncta);
+  for (int c = 0; c < pl->ncta; ++c) {
+    desc[4 * c] = pl->cta_wt0[c]; desc[4 * c + 1] = pl->cta_wt0[c + 1]; desc[4 * c + 2] = pl->cta_bkt0[c];
+    desc[4 * c + 3] = pl->bkt_tile[(size_t)pl->cta_bkt0[c]];
   }
   UP(e->ell_cta_desc, desc, int32_t);
 #undef UP
   cudaError_t se = cudaStreamSynchronize(st);  // the host vectors die with this frame
   if (se != cudaSuccess) { ell_free(e); return (int)se; }
-  e->kind = 3; e->m_hint = m; e->rb = rb; e->ell_nrec = h.nrec; e->ell_ncta = h.ncta; e->nbkt = nbkt;
-  e->nbytes += (int64_t)h.rec.size() + 4 * (h.nrec + 1) + 4ll * (2 * nbkt + 2 * h.ncta + 2);
+  e->kind = 3; e->m_hint = m; e->rb = rb; e->ell_nrec = pl->nrec; e->ell_ncta = pl->ncta; e->nbkt = nbkt;
+  e->nbytes += pl->rec_bytes + 4 * (pl->nrec + 1) + 4ll * (2 * nbkt + 4 * pl->ncta + 2);
   return 0;
 }
 
@@ -623,6 +883,29 @@ int ell_launch(const mde_edges* e, const float* X, int m, float* grad, int* nblo
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
+static int ell_export(const EllPlan& pl, const unsigned char* rec_host, int rb, int64_t nentries, mde_ell_host_t* out) {
+  memset(out, 0, sizeof(*out));
+  auto dup = [](const void* p_, size_t bytes) -> void* {
+    void* q = malloc(bytes ? bytes : 1);
+    if (q && bytes) memcpy(q, p_, bytes);
+    return q;
+  };
+  out->rec_bytes = pl.rec_bytes;
+  out->nrec = pl.nrec; out->nbkt = (int32_t)pl.bkt_tile.size(); out->ncta = pl.ncta; out->tile_rows_log2 = rb;
+  out->nslots = pl.nslots; out->nentries = nentries; out->npadded = pl.npadded;
+  out->rec = (unsigned char*)dup(rec_host, (size_t)pl.rec_bytes);
+  out->rec_off = (uint32_t*)dup(pl.rec_off.data(), 4 * pl.rec_off.size());
+  out->bkt_tile = (int32_t*)dup(pl.bkt_tile.data(), 4 * pl.bkt_tile.size());
+  out->bkt_wt0 = (int32_t*)dup(pl.bkt_wt0.data(), 4 * pl.bkt_wt0.size());
+  out->cta_wt0 = (int32_t*)dup(pl.cta_wt0.data(), 4 * pl.cta_wt0.size());
+  out->cta_bkt0 = (int32_t*)dup(pl.cta_bkt0.data(), 4 * pl.cta_bkt0.size());
+  if (!out->rec || !out->rec_off || !out->bkt_tile || !out->bkt_wt0 || !out->cta_wt0 || !out->cta_bkt0) {
+    mde_ell_host_free(out);
+    return MDE_E_ALLOC;
+  }
+  return 0;
+}
+
 int mde_ell_host_layout(int64_t n_items, int64_t p, int embedding_dim, const int32_t* src, const int32_t* dst,
                         const float* par0, int push_pull, int tile_rows_log2, int max_cta, mde_ell_host_t* out) {
   if (!src || !dst || !par0 || !out) return MDE_E_INVALID;
@@ -630,26 +913,24 @@ int mde_ell_host_layout(int64_t n_items, int64_t p, int embedding_dim, const int
   const int rb = tile_rows_log2 > 0 ? tile_rows_log2 : ell_default_rb(embedding_dim);
   const int rc = ell_build_host(n_items, p, embedding_dim, src, dst, par0, push_pull, rb, max_cta > 0 ? max_cta : kNumSMs, h);
   if (rc) return rc;
-  memset(out, 0, sizeof(*out));
-  auto dup = [](const void* p_, size_t bytes) -> void* {
-    void* q = malloc(bytes ? bytes : 1);
-    if (q && bytes) memcpy(q, p_, bytes);
-    return q;
-  };
-  out->rec_bytes = (int64_t)h.rec.size();
-  out->nrec = h.nrec; out->nbkt = (int32_t)h.bkt_tile.size(); out->ncta = h.ncta; out->tile_rows_log2 = h.rb;
-  out->nslots = h.nslots; out->nentries = h.nentries; out->npadded = h.npadded;
-  out->rec = (unsigned char*)dup(h.rec.data(), h.rec.size());
-  out->rec_off = (uint32_t*)dup(h.rec_off.data(), 4 * h.rec_off.size());
-  out->bkt_tile = (int32_t*)dup(h.bkt_tile.data(), 4 * h.bkt_tile.size());
-  out->bkt_wt0 = (int32_t*)dup(h.bkt_wt0.data(), 4 * h.bkt_wt0.size());
-  out->cta_wt0 = (int32_t*)dup(h.cta_wt0.data(), 4 * h.cta_wt0.size());
-  out->cta_bkt0 = (int32_t*)dup(h.cta_bkt0.data(), 4 * h.cta_bkt0.size());
-  if (!out->rec || !out->rec_off || !out->bkt_tile || !out->bkt_wt0 || !out->cta_wt0 || !out->cta_bkt0) {
-    mde_ell_host_free(out);
-    return MDE_E_ALLOC;
-  }
-  return 0;
+  return ell_export(h.plan, h.rec.data(), h.rb, h.nentries, out);
+}
+
+int mde_ell_device_layout(int64_t n_items, int64_t p, int embedding_dim, const int32_t* src, const int32_t* dst,
+                          const float* par0, int push_pull, int tile_rows_log2, int max_cta, mde_ell_host_t* out,
+                          void* stream) {
+  if (!src || !dst || !par0 || !out) return MDE_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  mde::EllDev d;
+  const int rb = tile_rows_log2 > 0 ? tile_rows_log2 : ell_default_rb(embedding_dim);
+  int rc = mde::ell_build_device(n_items, p, embedding_dim, src, dst, par0, push_pull, rb, max_cta > 0 ? max_cta : kNumSMs, d, st);
+  if (rc) return rc;
+  std::vector<unsigned char> host((size_t)d.plan.rec_bytes);
+  cudaError_t ce = cudaMemcpyAsync(host.data(), d.rec, host.size(), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  cudaFree(d.rec);
+  if (ce != cudaSuccess) return (int)ce;
+  return ell_export(d.plan, host.data(), d.rb, d.nentries, out);
 }
 
 void mde_ell_host_free(mde_ell_host_t* h) {
