@@ -113,9 +113,12 @@ __device__ __forceinline__ void eval_fn_t(float s0, float s1, float d, float a, 
     float r = a - d; f = b * r * r; fp = 2.0f * b * (d - a);
   }
   else if constexpr (FN == MDE_FN_L_HUBER) {
-    float r = fabsf(a - d);
-      if (r < s0) { f = r * r; fp = 2.0f * (d - a); }
-      else { f = s0 * (2.0f * r - s0); fp = 2.0f * s0 * signf(d - a); }
+    // branch-free, same values: c = clamp(d - a, -s0, s0); |e| < s0: f = e (2e - e) = e^2, f' = 2e;
+    // otherwise f = s0 (2|e| - s0), f' = 2 s0 sign(e)   (losses.py:101-125)
+    const float e = d - a;
+    const float c = fminf(fmaxf(e, -s0), s0);
+    f = c * (2.0f * e - c);
+    fp = 2.0f * c;
   }
   else if constexpr (FN == MDE_FN_L_CUBIC) {
     float r = fabsf(a - d); f = r * r * r; fp = 3.0f * r * r * signf(d - a);

@@ -339,7 +339,16 @@ __device__ __forceinline__ void ell_fast_coeff(float d2, float w, float& flog2, 
   }
 }
 
-template <int M, int FA, int FR, bool FAST, int CLS>
+// f' of these functions is finite at d = 0, so g = f'/(p d) can be formed from a clamped rsqrt without any guard
+// (at d = 0 the difference vector is 0 and a finite g contributes nothing, like the reference's replacement value)
+template <int FA, int FR>
+struct EllFiniteAtZero {
+  static constexpr bool value = (FA == FR) && (FA == MDE_FN_L_HUBER || FA == MDE_FN_L_QUADRATIC || FA == MDE_FN_P_QUADRATIC);
+};
+
+// MASK: the lane-slot row has pads (entries e >= cnt) that the generic functions must not see; rows whose 32 lane-slots
+// all hold W entries (almost all of them: lane-slots are sorted by length) run without the two selects
+template <int M, int FA, int FR, bool FAST, int CLS, bool MASK>
 __device__ __forceinline__ void ell_entry(const EllArgs& a, const float* __restrict__ Xt, const float (&xi)[M], float w,
                                           uint32_t j, bool valid, float (&acc)[M], float& lf) {
   float xj[M], diff[M];
@@ -351,16 +360,25 @@ __device__ __forceinline__ void ell_entry(const EllArgs& a, const float* __restr
   if constexpr (FAST) {
     ell_fast_coeff<CLS>(d2, w, f, g);  // pads: w = 0
   } else {
-    // d and 1/d from ONE rsqrt.approx (<= 2 ulp) instead of an IEEE sqrt and an IEEE division (18 instructions);
-    // d = 0: g is non-finite -> 1 like the reference (average_distortion.py:55-62), the difference vector is 0
-    const float rs = fast_rsqrt(d2);
-    const float d = (d2 > 0.0f) ? d2 * rs : 0.0f;
+    // d and 1/d from ONE rsqrt.approx (<= 2 ulp) instead of an IEEE sqrt and an IEEE division (18 instructions)
     float fp;
-    edge_f_fp<FA, FR>(a.fn, d, w, 0.0f, f, fp);
-    g = (fp * a.inv_p) * rs;
-    if (!isfinite(g)) g = 1.0f;
-    f = valid ? f : 0.0f;
-    g = valid ? g : 0.0f;
+    if constexpr (EllFiniteAtZero<FA, FR>::value) {
+      const float rs = fast_rsqrt(fmaxf(d2, 1e-30f));
+      const float d = d2 * rs;
+      edge_f_fp<FA, FR>(a.fn, d, w, 0.0f, f, fp);
+      g = (fp * a.inv_p) * rs;
+    } else {
+      // d = 0: g is non-finite -> 1 like the reference (average_distortion.py:55-62), the difference vector is 0
+      const float rs = fast_rsqrt(d2);
+      const float d = (d2 > 0.0f) ? d2 * rs : 0.0f;
+      edge_f_fp<FA, FR>(a.fn, d, w, 0.0f, f, fp);
+      g = (fp * a.inv_p) * rs;
+      if (!isfinite(g)) g = 1.0f;
+    }
+    if constexpr (MASK) {
+      f = valid ? f : 0.0f;
+      g = valid ? g : 0.0f;
+    }
   }
   lf += f;
 #pragma unroll
@@ -368,7 +386,7 @@ __device__ __forceinline__ void ell_entry(const EllArgs& a, const float* __restr
 }
 
 // all W entries of this lane's lane-slot, straight from the shared-memory slot
-template <int M, int FA, int FR, bool FAST, int CLS>
+template <int M, int FA, int FR, bool FAST, int CLS, bool MASK>
 __device__ __forceinline__ void ell_columns(const EllArgs& a, const float* __restrict__ Xt, const unsigned char* cols,
                                             int lane, int W, int cnt, const float (&xi)[M], float (&acc)[M],
                                             float& lf) {
@@ -378,8 +396,8 @@ __device__ __forceinline__ void ell_columns(const EllArgs& a, const float* __res
   for (int c2 = 0; 2 * c2 < W; ++c2) {
     const float2 w2 = wp[c2 * (kEllPair / 8)];
     const uint32_t ix = ip[c2 * (kEllPair / 4)];
-    ell_entry<M, FA, FR, FAST, CLS>(a, Xt, xi, w2.x, ix & 0xffffu, 2 * c2 < cnt, acc, lf);
-    ell_entry<M, FA, FR, FAST, CLS>(a, Xt, xi, w2.y, ix >> 16, 2 * c2 + 1 < cnt, acc, lf);
+    ell_entry<M, FA, FR, FAST, CLS, MASK>(a, Xt, xi, w2.x, ix & 0xffffu, 2 * c2 < cnt, acc, lf);
+    ell_entry<M, FA, FR, FAST, CLS, MASK>(a, Xt, xi, w2.y, ix >> 16, 2 * c2 + 1 < cnt, acc, lf);
   }
 }
 
@@ -506,13 +524,15 @@ distortion_ell_kernel(const EllArgs a) {
       for (int q = 0; q < M; ++q) acc[q] = 0.0f;
       float lf = 0.0f;
       if (FAST) {
-        if (hdr.y == 0) ell_columns<M, FA, FR, true, 0>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
-        else ell_columns<M, FA, FR, true, 1>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
+        if (hdr.y == 0) ell_columns<M, FA, FR, true, 0, false>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
+        else ell_columns<M, FA, FR, true, 1, false>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
         const float cc = hdr.y == 0 ? c_att : a.inv_p;  // the class constant of f'/(p d), once per lane-slot
 #pragma unroll
         for (int q = 0; q < M; ++q) acc[q] *= cc;
+      } else if (__all_sync(kFull, cnt == W)) {  // warp-uniform: no pads in this row
+        ell_columns<M, FA, FR, false, 2, false>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
       } else {
-        ell_columns<M, FA, FR, false, 2>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
+        ell_columns<M, FA, FR, false, 2, true>(a, Xt, cols + k * row_bytes, lane, W, cnt, xi, acc, lf);
       }
       if (!(ow >> 31)) e_red_row<M>(a.grad, own, acc);
       lrec += lf;
