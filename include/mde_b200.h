@@ -91,9 +91,11 @@ uint64_t mde_launch_count(void);
 int mde_edges_create(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t n_items,
                      const float* par0, const float* par1 /* nullable */, const mde_fn_t* fn,
                      int64_t p_total, void* stream);
-/* Same, with the embedding dimension: for embedding_dim <= 4 dense graphs (>= 64 edges per item) get the
- * tile-resident layout (pymde_b200/csrc/mde_pull.cu: vertex tiles of X live in shared memory, the edge records are
- * streamed by TMA); everything else keeps the sorted-SoA layout. */
+/* Same, with the embedding dimension: for embedding_dim <= 4 dense graphs (>= 64 edges per item) get a tile-resident
+ * layout next to the sorted-SoA arrays -- the ELL pull records of pymde_b200/csrc/mde_ell.cu (one lane per owner: vertex
+ * tiles of X live in shared memory, the records are streamed by TMA, built on the device), or the flat pull records of
+ * mde_pull.cu when the ELL builder refuses the shape (more than 32 vertex tiles); everything else keeps the sorted-SoA
+ * layout alone. */
 int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int64_t n_items,
                         const float* par0, const float* par1 /* nullable */, const mde_fn_t* fn,
                         int64_t p_total, int embedding_dim, void* stream);

@@ -1,7 +1,7 @@
 // mde_edges.cuh -- the device-resident edge layout shared by mde_edges.cu (layout build, strided / quad / wide
 // kernels, per-edge outputs) and mde_tiled.cu (tile-resident kernel).
 //
-// Two layouts (one per shard, chosen at mde_edges_create_ex):
+// Layouts (one per shard, chosen at mde_edges_create_ex):
 //
 //  kind 0  "sorted SoA"     src[p], dst[p], par0[p] (, par1[p]) sorted by (class, src, dst); perm[p].
 //                           Any m; the m >= 5 kernels, WeightedQuadratic (par1) and very sparse graphs use it.
