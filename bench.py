@@ -350,6 +350,7 @@ def kernel_roofline(mde, X0d, m, p_local, n, torch, dev, lib, _lib, cold, profil
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None if prof is None else prof.get("dram_bytes"),
             "traffic_source": None if prof is None else prof.get("source"),
+            "ncu_duration_us": None if prof is None else prof.get("ncu_duration_us"),  # same capture, cold caches
             "peak_source": peak_src, "algorithmic_bytes": b_alg, "kernel_ms": k_ms,
             "timing": ("CUDA events around one launch, 512 MB L2 flush before each, mean of 20" if cold else
                        "CUDA events around one launch, inputs larger than L2, mean of 6")}

@@ -196,3 +196,24 @@ def test_unsupported_shapes_are_refused():
     assert build(100, 2, edges, w, False, rb=14)[0] == _lib.MDE_E_UNSUPPORTED  # u16 byte offsets overflow
     big, wb = random_problem(rng, 9000, 2000, False, False)
     assert build(9000, 2, big, wb, False, rb=8)[0] == _lib.MDE_E_UNSUPPORTED  # more than 32 neighbour tiles
+
+
+@pytest.mark.parametrize("pack", ["0", "1"])
+def test_packing_switch_changes_the_records_not_the_sums(pack, monkeypatch):
+    """MDE_B200_ELL_PACK=0 (one lane-slot per lane in every record, the A/B switch) holds the same entries."""
+    monkeypatch.setenv("MDE_B200_ELL_PACK", pack)
+    rng = np.random.default_rng(11)
+    n, m = 1500, 2
+    edges, w = random_problem(rng, n, 9000, True, False)
+    rc, lay = build(n, m, edges, w, True, 8)
+    assert rc == 0
+    recs = decode(lay, n, m)
+    X = rng.standard_normal((n, m))
+    pt = len(edges)
+    v_ref, g_ref = O.average_distortion(X, edges, O.FnSpec(O.P_QUADRATIC, w), True)
+    loss, grad = pull_sums(recs, X, lambda d2, ww, cls: (ww * d2, 2.0 * ww / pt), masked=False)
+    np.testing.assert_allclose(loss / pt, v_ref, rtol=1e-12)
+    np.testing.assert_allclose(grad, g_ref, rtol=1e-10, atol=1e-12 * np.abs(g_ref).max())
+    rec, off = lay["rec"], lay["rec_off"].astype(np.int64) * 16
+    ks = {int(np.frombuffer(rec[o + 8:o + 12].tobytes(), dtype=np.int32)[0]) for o in off[:-1]}
+    assert ks == {1} if pack == "0" else max(ks) > 1
