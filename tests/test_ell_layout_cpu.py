@@ -217,3 +217,28 @@ def test_packing_switch_changes_the_records_not_the_sums(pack, monkeypatch):
     rec, off = lay["rec"], lay["rec_off"].astype(np.int64) * 16
     ks = {int(np.frombuffer(rec[o + 8:o + 12].tobytes(), dtype=np.int32)[0]) for o in off[:-1]}
     assert ks == {1} if pack == "0" else max(ks) > 1
+
+
+def test_cta_ranges_are_cost_balanced_on_the_bench_workload():
+    """The persistent grid gets contiguous record ranges of equal estimated cost (per record / per lane-slot row / per
+    entry column instruction counts from the ncu source page, a tile load charged per bucket a range touches)."""
+    import bench
+    edges, w = bench.c2_edges(0)
+    e = np.sort(edges, axis=1)
+    rc, lay = build(bench.N_ITEMS, 2, e, w, True)
+    assert rc == 0 and lay["ncta"] == 148
+    rec, off = lay["rec"], lay["rec_off"].astype(np.int64) * 16
+    hdr = np.stack([np.frombuffer(rec[o:o + 16].tobytes(), dtype=np.int32) for o in off[:-1]])
+    W, cls, K = hdr[:, 0], hdr[:, 1], hdr[:, 2]
+    cost = 60 + K * (30 + W * np.where(cls == 1, 31, 23))
+    cw, bw = lay["cta_wt0"], lay["bkt_wt0"]
+    tot = []
+    for c in range(lay["ncta"]):
+        a, b = cw[c], cw[c + 1]
+        tiles = 1 + int(np.sum((bw[1:-1] > a) & (bw[1:-1] < b)))
+        tot.append(cost[a:b].sum() + 6000 * tiles if b > a else 0)
+    tot = np.array(tot, dtype=np.float64)
+    busy = tot[tot > 0]
+    assert len(busy) >= 146                      # at most the tail CTAs stay empty
+    assert busy.max() <= 1.12 * busy.mean(), (busy.max(), busy.mean())
+    assert lay["npadded"] <= 1.15 * lay["nentries"]  # pads: 11 % at C2
