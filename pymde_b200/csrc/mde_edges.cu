@@ -809,6 +809,10 @@ int mde_edges_create_ex(mde_edges_t** out, const int64_t* edges, int64_t p, int6
   if (want_ell) {
     // ELL pull records next to the sorted-SoA arrays (kind 3); MDE_E_UNSUPPORTED leaves the layout at kind 0
     rc = ell_build(e, fn, embedding_dim, st);
+    if (rc == (int)cudaErrorMemoryAllocation) {  // no room for the second layout: the sorted-SoA one is complete
+      (void)cudaGetLastError();
+      rc = MDE_E_UNSUPPORTED;
+    }
     if (rc != 0 && rc != MDE_E_UNSUPPORTED) goto fail;
     rc = 0;
   }
